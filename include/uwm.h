@@ -1,0 +1,151 @@
+/*
+ * uwm.h — C ABI of libuwm_b200.so: the B200 (sm_100a) implementation of the
+ * UNet watermark-mask inference hot path of Dave-he/unet-watermark.
+ *
+ * The reference has no FFI of its own: its seam is the Python nn.Module returned by
+ * `create_model_from_config(cfg)` (reference src/models/unet_model.py:93-120) and called as
+ * `self.model(input_tensor)` (reference src/predict.py:339, :611).  This header is the
+ * C-ABI a host binds *underneath* that seam; `unet_watermark_b200/unet_model.py` is the
+ * ctypes host that keeps the reference's Python surface.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers, ints, sizes.  No torch / C++ types.
+ *   - every pointer named `d_*` is a DEVICE pointer owned by the caller.
+ *   - activations are NHWC bf16 with an explicit pixel pitch (elements between
+ *     consecutive pixels, >= channels) so that a tensor can live inside a wider
+ *     concat buffer.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - every function returns 0 on success, a negative UWM_E* code otherwise, and
+ *     `uwm_last_error()` returns the message for the calling thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef UWM_H_
+#define UWM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UWM_OK            0
+#define UWM_EINVAL       -1   /* bad argument / unsupported shape            */
+#define UWM_ECUDA        -2   /* CUDA runtime / driver error                 */
+#define UWM_ENOMEM       -3   /* workspace allocation failed                 */
+#define UWM_ESTATE       -4   /* weights not set, wrong batch, ...           */
+
+/* input formats of uwm_model_forward / uwm_prep_input */
+#define UWM_IN_F32_NCHW   0   /* float32 [B,3,H,W], already ImageNet-normalised (what
+                                 get_val_transform feeds the net, reference src/utils/dataset.py:389-395) */
+#define UWM_IN_U8_NHWC    1   /* uint8  [B,H,W,3] RGB; (x/255-mean)/std fused on the GPU        */
+
+/* weight packing kinds reported by uwm_model_layer_desc */
+#define UWM_PACK_TAPS     0   /* [cout_pad][kh*kw][cin] bf16, K index = (kh*kw_idx)*cin + c      */
+#define UWM_PACK_STEM_S2D 1   /* 7x7/s2 stem as 4x4/s1 over the 2x2 space-to-depth input:
+                                 [64][4*4][16] bf16, channel = (ph*2+pw)*3 + c, 12..15 zero      */
+
+const char* uwm_last_error(void);
+int         uwm_abi_version(void);
+/* number of CUDA kernels launched by this library in this process so far */
+uint64_t    uwm_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Single operators (the kernels of the path, callable on their own; the parity tests drive
+ * every distinct layer shape through these).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores.
+ * Replaces nn.Conv2d(+folded BatchNorm2d)(+residual add)(+ReLU) as used by torchvision
+ * BasicBlock/Bottleneck and smp Conv2dReLU.
+ *   x   : [n,h,w,cin]  bf16, pixel pitch x_pitch
+ *   wgt : [cout_pad][kh*kw*cin] bf16 (UWM_PACK_TAPS), cout_pad = cout rounded up to 16
+ *   bias: [cout_pad] fp32
+ *   res : optional [n,ho,wo,cout] bf16 added before ReLU (pitch res_pitch), or NULL
+ *   y   : [n,ho,wo,cout] bf16, pitch y_pitch;  ho = (h+2*pad-kh)/stride+1
+ * cin must be a multiple of 16, cout a multiple of 16, stride 1 or 2. */
+int uwm_conv2d_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                         const void* d_wgt, const float* d_bias, int cout,
+                         int kh, int kw, int stride, int pad,
+                         const void* d_res, int res_pitch, int relu,
+                         void* d_y, int y_pitch, void* stream);
+
+/* Segmentation head: conv3x3(cin -> 1, bias) + optional sigmoid + threshold + uint8 mask.
+ * Replaces smp SegmentationHead and `(mask > thr)*255`
+ * (reference src/predict.py:624-625).  d_logits (fp32 [n,h,w]) and d_mask (uint8 [n,h,w],
+ * values 0/255) may each be NULL.  thr_logit is compared against the raw logit. */
+int uwm_head_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                       const void* d_wgt /*[16][9*cin]*/, const float* d_bias /*[16]*/,
+                       float* d_logits, int apply_sigmoid, uint8_t* d_mask, float thr_logit,
+                       void* stream);
+
+/* MaxPool2d(3, stride 2, padding 1) — torchvision ResNet stem pool. */
+int uwm_maxpool3x3s2_nhwc_bf16(const void* d_x, int n, int h, int w, int c, int x_pitch,
+                               void* d_y, int y_pitch, void* stream);
+
+/* F.interpolate(scale_factor=2, mode="nearest") written into channels [0,c) of a (possibly
+ * wider, pitch y_pitch) buffer — smp DecoderBlock's upsample fused with the concat
+ * (the skip half is written in place by its producer). */
+int uwm_upsample2x_nhwc_bf16(const void* d_x, int n, int h, int w, int c, int x_pitch,
+                             void* d_y, int y_pitch, void* stream);
+
+/* Input preparation: normalise (u8) / cast (f32) + 2x2 space-to-depth to bf16
+ * [n,h/2,w/2,16].  Replaces the Normalize+ToTensorV2 half of get_val_transform. */
+int uwm_prep_input(const void* d_in, int in_fmt, int n, int h, int w, void* d_y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-model plan: smp.Unet(resnet34|resnet50, depth 5) forward.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct uwm_model uwm_model;
+
+typedef struct uwm_layer_desc {
+  char    conv_key[96];   /* state-dict prefix of the conv, e.g. "encoder.layer1.0.conv1"     */
+  char    bn_key[96];     /* prefix of the BatchNorm folded into it, "" if the conv has bias  */
+  int32_t cin, cout, cout_pad, kh, kw, stride, pad;
+  int32_t pack;           /* UWM_PACK_*                                                      */
+  int32_t relu, has_residual;
+  int64_t w_elems;        /* bf16 elements expected by uwm_model_set_layer                   */
+  int64_t b_elems;        /* fp32 elements expected                                           */
+  double  flops_per_image;/* 2*MACs of the reference conv (algorithmic, un-padded)            */
+} uwm_layer_desc;
+
+/* encoder: 34 or 50.  decoder_channels: 5 ints (smp default 256,128,64,32,16).
+ * H,W: network input size, both divisible by 32.  Allocates the activation workspace for
+ * max_batch images on the current device. */
+int    uwm_model_create(int encoder, const int* decoder_channels, int h, int w, int max_batch,
+                        uwm_model** out);
+int    uwm_model_destroy(uwm_model* m);
+int    uwm_model_num_layers(const uwm_model* m);
+int    uwm_model_layer_desc(const uwm_model* m, int i, uwm_layer_desc* d);
+/* copies host-or-device packed weights into library-owned device memory */
+int    uwm_model_set_layer(uwm_model* m, int i, const void* wgt_bf16, int64_t w_elems,
+                           const float* bias, int64_t b_elems);
+size_t uwm_model_workspace_bytes(const uwm_model* m);
+int    uwm_model_num_kernels(const uwm_model* m);       /* launches per forward             */
+double uwm_model_flops_per_image(const uwm_model* m);   /* algorithmic conv FLOPs           */
+
+/* One forward pass for `batch` (<= max_batch) images.
+ *   d_in     : UWM_IN_F32_NCHW or UWM_IN_U8_NHWC
+ *   d_logits : fp32 [batch,1,H,W] (raw logits, or probabilities if apply_sigmoid) or NULL
+ *   d_mask   : uint8 [batch,H,W] 0/255 where logit > thr_logit, or NULL
+ * use_graph != 0 replays a cached CUDA graph (captured on first use per argument set). */
+int    uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int batch,
+                         float* d_logits, int apply_sigmoid, uint8_t* d_mask, float thr_logit,
+                         int use_graph, void* stream);
+
+/* Debug/parity tap: copy the bf16 NHWC output of plan tensor `name` (e.g. "encoder.layer1",
+ * "decoder.blocks.0") for the last forward into d_dst as dense [batch,h,w,c]; returns dims. */
+int    uwm_model_read_tensor(uwm_model* m, const char* name, int batch, void* d_dst,
+                             int64_t dst_bytes, int* h, int* w, int* c, void* stream);
+
+/* Per-kernel device timing of one eager forward (CUDA events around every launch).
+ * names: caller buffer of n_max*64 chars; ms: n_max floats.  Returns number of kernels. */
+int    uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int batch,
+                         float* d_logits, uint8_t* d_mask, float thr_logit,
+                         char* names, float* ms, double* flops, double* bytes, int n_max,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWM_H_ */

@@ -1,0 +1,40 @@
+"""Shared per-operator parity cases (used by tests/test_ops_gpu.py and tools/gpu_op_check.py).
+
+Every distinct conv geometry of Unet-resnet34/50 appears here at a reduced
+spatial size / batch so the torch fp32 reference finishes instantly.
+"""
+# (name, n, h, w, cin, cout, k, stride, pad, relu, residual, in_pitch_extra, out_pitch_extra)
+CONV_CASES = [
+    ("l1_3x3_64_64",        2, 32, 32,   64,  64, 3, 1, 1, True,  False, 0, 0),
+    ("l1_3x3_64_64_res",    2, 32, 32,   64,  64, 3, 1, 1, True,  True,  0, 0),
+    ("l2_3x3s2_64_128",     2, 32, 32,   64, 128, 3, 2, 1, True,  False, 0, 0),
+    ("l2_ds_1x1s2_64_128",  2, 32, 32,   64, 128, 1, 2, 0, False, False, 0, 0),
+    ("l2_3x3_128_128_res",  2, 16, 16,  128, 128, 3, 1, 1, True,  True,  0, 0),
+    ("l3_3x3s2_128_256",    2, 16, 16,  128, 256, 3, 2, 1, True,  False, 0, 0),
+    ("l3_3x3_256_256_res",  2,  8,  8,  256, 256, 3, 1, 1, True,  True,  0, 0),
+    ("l4_3x3s2_256_512",    4,  8,  8,  256, 512, 3, 2, 1, True,  False, 0, 0),
+    ("l4_ds_1x1s2_256_512", 4,  8,  8,  256, 512, 1, 2, 0, False, False, 0, 0),
+    ("l4_3x3_512_512_res",  4,  4,  4,  512, 512, 3, 1, 1, True,  True,  0, 0),
+    ("d0_3x3_768_256",      2,  8,  8,  768, 256, 3, 1, 1, True,  False, 0, 0),
+    ("d1_3x3_384_128",      1, 16, 16,  384, 128, 3, 1, 1, True,  False, 0, 0),
+    ("d2_3x3_192_64",       1, 32, 32,  192,  64, 3, 1, 1, True,  False, 0, 0),
+    ("d3_3x3_128_32",       1, 64, 64,  128,  32, 3, 1, 1, True,  False, 0, 0),
+    ("d3_3x3_32_32",        1, 64, 64,   32,  32, 3, 1, 1, True,  False, 0, 0),
+    ("d4_3x3_32_16",        1, 64, 128,  32,  16, 3, 1, 1, True,  False, 0, 0),
+    ("d4_3x3_16_16",        1, 64, 128,  16,  16, 3, 1, 1, True,  False, 0, 0),
+    # pitched views: input is a channel slice of a wider buffer, output lands inside a concat buffer
+    ("pitched_in_out",      2, 16, 16,   64,  64, 3, 1, 1, True,  True,  64, 128),
+    ("pitched_s2",          2, 16, 16,   64, 128, 3, 2, 1, True,  False, 32, 64),
+    # ragged: spatial sizes that do not tile evenly (768-input pyramid: 24, 48, 96)
+    ("ragged_24",           3, 24, 24,  128, 128, 3, 1, 1, True,  True,  0, 0),
+    ("ragged_24_s2",        3, 24, 24,  128, 256, 3, 2, 1, True,  False, 0, 0),
+    ("ragged_48x24",        1, 48, 24,   64,  96, 3, 1, 1, False, False, 0, 0),
+    ("tiny_1x1_spatial",    5,  1,  1,  512, 512, 3, 1, 1, True,  True,  0, 0),
+    ("tiny_2x2_s2",         3,  2,  2,  256, 512, 3, 2, 1, True,  False, 0, 0),
+    # resnet50 bottleneck 1x1s and the big decoder K
+    ("r50_1x1_64_256",      1, 32, 32,   64, 256, 1, 1, 0, False, False, 0, 0),
+    ("r50_1x1_256_64",      1, 32, 32,  256,  64, 1, 1, 0, True,  False, 0, 0),
+    ("r50_1x1_1024_2048s2", 1,  8,  8, 1024, 2048, 1, 2, 0, False, False, 0, 0),
+    ("r50_1x1_512_2048res", 1,  4,  4,  512, 2048, 1, 1, 0, True,  True,  0, 0),
+    ("r50_d0_3x3_3072_256", 1,  8,  8, 3072, 256, 3, 1, 1, True,  False, 0, 0),
+]

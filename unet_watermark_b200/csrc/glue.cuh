@@ -1,0 +1,147 @@
+// HBM-bound glue kernels of the path: input preparation, stem max-pool, nearest-2x upsample.
+// All are pure streaming kernels: 16-byte vector accesses, consecutive threads on consecutive
+// addresses, grid-stride loops sized to a multiple of the SM count.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uwm {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: network input -> bf16 2x2 space-to-depth tensor [n, h/2, w/2, 16]
+//   channel (ph*2+pw)*3 + c  = x[c, 2i+ph, 2j+pw];  channels 12..15 = 0.
+// The 7x7/s2/p3 stem conv becomes a 4x4/s1 conv over this tensor (taps -2..1).
+// u8 input fuses get_val_transform's Normalize: (x/255 - mean)/std, computed in fp32.
+// One thread per output pixel (32 bytes out).
+// ---------------------------------------------------------------------------------------------
+template <bool kU8>
+__global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ in,
+                                                       __nv_bfloat16* __restrict__ out, int n,
+                                                       int h, int w) {
+  const int h2 = h >> 1, w2 = w >> 1;
+  const long long total = (long long)n * h2 * w2;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % w2);
+    const int i = (int)((idx / w2) % h2);
+    const int b = (int)(idx / ((long long)w2 * h2));
+    float v[16];
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = 0.f;
+    if (kU8) {
+      const uint8_t* src = static_cast<const uint8_t*>(in);
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        // 2 pixels x 3 channels = 6 consecutive bytes
+        const uint8_t* r = src + (((long long)b * h + (2 * i + ph)) * w + 2 * j) * 3;
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            // same operation order as albumentations Normalize: (x/255 - mean)/std, in fp32
+            const float x = (float)r[pw * 3 + c];
+            v[(ph * 2 + pw) * 3 + c] = (x * (1.0f / 255.0f) - mean[c]) / stdv[c];
+          }
+      }
+    } else {
+      const float* src = static_cast<const float*>(in);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const float2 t = *reinterpret_cast<const float2*>(
+              src + (((long long)b * 3 + c) * h + (2 * i + ph)) * w + 2 * j);
+          v[(ph * 2 + 0) * 3 + c] = t.x;
+          v[(ph * 2 + 1) * 3 + c] = t.y;
+        }
+    }
+    uint4 o0, o1;
+    o0.x = pack2(v[0], v[1]);   o0.y = pack2(v[2], v[3]);
+    o0.z = pack2(v[4], v[5]);   o0.w = pack2(v[6], v[7]);
+    o1.x = pack2(v[8], v[9]);   o1.y = pack2(v[10], v[11]);
+    o1.z = pack2(v[12], v[13]); o1.w = pack2(v[14], v[15]);
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* ra = reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162* rb = reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rr[i] = __hmax2(ra[i], rb[i]);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, padding 1), NHWC bf16.  Padding is -inf (PyTorch semantics):
+// out-of-range taps are skipped.  One thread per (output pixel, 8-channel group).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x,
+                                                           __nv_bfloat16* __restrict__ y, int n,
+                                                           int h, int w, int c, long long x_pitch,
+                                                           long long y_pitch) {
+  const int ho = h >> 1, wo = w >> 1, cg = c >> 3;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long t = idx / cg;
+    const int j = (int)(t % wo); t /= wo;
+    const int i = (int)(t % ho);
+    const int b = (int)(t / ho);
+    uint4 m;
+    bool first = true;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int ih = 2 * i + dh;
+      if (ih < 0 || ih >= h) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int iw = 2 * j + dw;
+        if (iw < 0 || iw >= w) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(
+            x + (((long long)b * h + ih) * w + iw) * x_pitch + g * 8);
+        m = first ? v : hmax8(m, v);
+        first = false;
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((long long)b * ho + i) * wo + j) * y_pitch + g * 8) = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Nearest 2x upsample into channels [0,c) of a pitch-y_pitch buffer:
+//   y[b, i, j, 0:c] = x[b, i/2, j/2, 0:c].   One thread per (output pixel, 8-channel group).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         __nv_bfloat16* __restrict__ y, int n,
+                                                         int h, int w, int c, long long x_pitch,
+                                                         long long y_pitch) {
+  const int ho = h * 2, wo = w * 2, cg = c >> 3;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long t = idx / cg;
+    const int j = (int)(t % wo); t /= wo;
+    const int i = (int)(t % ho);
+    const int b = (int)(t / ho);
+    const uint4 v = *reinterpret_cast<const uint4*>(
+        x + (((long long)b * h + (i >> 1)) * w + (j >> 1)) * x_pitch + g * 8);
+    *reinterpret_cast<uint4*>(y + (((long long)b * ho + i) * wo + j) * y_pitch + g * 8) = v;
+  }
+}
+
+}  // namespace uwm

@@ -1,0 +1,819 @@
+// libuwm_b200.so — C ABI (include/uwm.h) over the sm_100a kernels in conv_tc.cuh / glue.cuh.
+//
+// Host side of the hot path: tensor-map construction, tile selection, the static plan of
+// smp.Unet(resnet34|resnet50), the activation arena and CUDA-graph replay.
+// libcuda is NOT linked: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint so
+// the library still loads (and exports its symbols) on a machine without a GPU driver.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/uwm.h"
+#include "conv_tc.cuh"
+#include "glue.cuh"
+
+using namespace uwm;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(UWM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+static bool debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UWM_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static int post_launch(const char* what, cudaStream_t st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(UWM_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  if (debug_sync()) {
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(UWM_ECUDA, "%s faulted: %s", what, cudaGetErrorString(e));
+  }
+  return UWM_OK;
+}
+
+extern "C" const char* uwm_last_error(void) { return g_err; }
+extern "C" int uwm_abi_version(void) { return 1; }
+extern "C" uint64_t uwm_kernel_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// driver entry point (no libcuda link)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv launch construction
+// ------------------------------------------------------------------------------------------
+struct ConvSpec {
+  const void* x = nullptr;        // activation base (already offset to the channel slice)
+  int n = 0, h = 0, w = 0, cin = 0;
+  long long x_pitch = 0;
+  const void* wgt = nullptr;      // [cout_pad][ntaps*cin]
+  const float* bias = nullptr;
+  int cout = 0, cout_pad = 0;
+  int ntaps = 0;
+  int8_t dh[kMaxTaps] = {0}, dw[kMaxTaps] = {0};
+  int stride = 1;
+  int h_out = 0, w_out = 0;
+  const void* res = nullptr;
+  long long res_pitch = 0;
+  int relu = 0;
+  void* out = nullptr;
+  long long out_pitch = 0;
+  int head = 0, apply_sigmoid = 0;
+  float* logits = nullptr;
+  uint8_t* mask = nullptr;
+  float thr_logit = 0.f;
+};
+
+struct ConvLaunch {
+  CUtensorMap tm_act, tm_wgt;
+  ConvKArgs args;
+  unsigned grid = 0;
+  size_t smem = 0;
+};
+
+static void choose_tile(int W, int H, int N, int stride, int* tw, int* th, int* tn) {
+  double best = -1.0;
+  for (int a = 128; a >= 1; a >>= 1) {
+    if (a * stride > 256) continue;
+    for (int b = 128 / a; b >= 1; b >>= 1) {
+      if (b * stride > 256) continue;
+      const int c = 128 / (a * b);
+      if (c > 256) continue;
+      const double cover = (double)((W + a - 1) / a * a) * ((H + b - 1) / b * b) * ((N + c - 1) / c * c);
+      const double eff = (double)W * H * N / cover;
+      // prefer full tiles, then wide rows (coalesced epilogue), then tall tiles over batch tiles
+      const double score = eff + 1e-4 * std::log2((double)a) + 1e-6 * std::log2((double)b);
+      if (score > best) { best = score; *tw = a; *th = b; *tn = c; }
+    }
+  }
+}
+
+static int build_conv(const ConvSpec& s, ConvLaunch* L) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if (s.cin % 16) return fail(UWM_EINVAL, "conv: cin=%d must be a multiple of 16", s.cin);
+  if (s.cout_pad % 16) return fail(UWM_EINVAL, "conv: cout_pad=%d must be a multiple of 16", s.cout_pad);
+  if (s.ntaps < 1 || s.ntaps > kMaxTaps) return fail(UWM_EINVAL, "conv: %d taps unsupported", s.ntaps);
+  if (s.stride != 1 && s.stride != 2) return fail(UWM_EINVAL, "conv: stride %d unsupported", s.stride);
+  if ((s.x_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.x) & 15))
+    return fail(UWM_EINVAL, "conv: activation base/pitch must be 16-byte aligned");
+  if (!s.head && ((s.out_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.out) & 15)))
+    return fail(UWM_EINVAL, "conv: output base/pitch must be 16-byte aligned");
+  if (s.res && ((s.res_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.res) & 15)))
+    return fail(UWM_EINVAL, "conv: residual base/pitch must be 16-byte aligned");
+
+  ConvKArgs& a = L->args;
+  memset(&a, 0, sizeof(a));
+  a.n_img = s.n; a.h_out = s.h_out; a.w_out = s.w_out;
+  choose_tile(s.w_out, s.h_out, s.n, s.stride, &a.tw, &a.th, &a.tn);
+  a.tiles_w = (s.w_out + a.tw - 1) / a.tw;
+  a.tiles_h = (s.h_out + a.th - 1) / a.th;
+  a.tiles_n = (s.n + a.tn - 1) / a.tn;
+  a.stride = s.stride;
+  a.kc = (s.cin % 64 == 0) ? 64 : (s.cin % 32 == 0) ? 32 : 16;
+  a.chunks = s.cin / a.kc;
+  a.ntaps = s.ntaps;
+  for (int t = 0; t < s.ntaps; ++t) { a.tap_dh[t] = s.dh[t]; a.tap_dw[t] = s.dw[t]; }
+  int bn = std::min(s.cout_pad, 128);
+  while (s.cout_pad % bn) bn -= 16;
+  a.block_n = bn;
+  a.n_tiles = s.cout_pad / bn;
+  a.cout = s.cout;
+  a.a_stage_bytes = 128u * a.kc * 2u;
+  a.b_stage_bytes = ((uint32_t)bn * a.kc * 2u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
+  int stages = (int)((96u * 1024u) / stage_bytes);
+  stages = std::max(2, std::min(stages, 12));
+  stages = std::min(stages, std::max(2, s.ntaps * a.chunks));
+  a.stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)bn) cols <<= 1;
+  a.tmem_cols = cols;
+  a.layout_type = (a.kc == 64) ? kLayoutSw128 : (a.kc == 32) ? kLayoutSw64 : kLayoutSw32;
+  a.bias = s.bias;
+  a.res = static_cast<const __nv_bfloat16*>(s.res);
+  a.out = static_cast<__nv_bfloat16*>(s.out);
+  a.res_pitch = s.res_pitch; a.out_pitch = s.out_pitch;
+  a.relu = s.relu;
+  a.head = s.head; a.apply_sigmoid = s.apply_sigmoid;
+  a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
+
+  L->grid = (unsigned)(a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles);
+  L->smem = 1024 /*align slack*/ + (size_t)stages * stage_bytes + 1024 /*bias*/ + 512 /*barriers*/;
+
+  const CUtensorMapSwizzle sw = (a.kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (a.kc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                             : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
+    cuuint64_t strides[3] = {(cuuint64_t)s.x_pitch * 2, (cuuint64_t)s.w * s.x_pitch * 2,
+                             (cuuint64_t)s.h * s.w * s.x_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)a.kc, (cuuint32_t)(a.tw * s.stride),
+                         (cuuint32_t)(a.th * s.stride), (cuuint32_t)a.tn};
+    cuuint32_t est[4] = {1, (cuuint32_t)s.stride, (cuuint32_t)s.stride, 1};
+    CUresult r = enc(&L->tm_act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.x), dims,
+                     strides, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(act) -> %d (c=%d w=%d h=%d n=%d pitch=%lld box=%u,%u,%u,%u)",
+                  (int)r, s.cin, s.w, s.h, s.n, s.x_pitch, box[0], box[1], box[2], box[3]);
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)s.ntaps * s.cin;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)s.cout_pad};
+    cuuint64_t strides[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)a.kc, (cuuint32_t)bn};
+    cuuint32_t est[2] = {1, 1};
+    CUresult r = enc(&L->tm_wgt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims,
+                     strides, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(wgt) -> %d (k=%llu cout=%d)", (int)r,
+                  (unsigned long long)ktot, s.cout_pad);
+  }
+  return UWM_OK;
+}
+
+static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args);
+  return post_launch("conv_tc_kernel", st);
+}
+
+static void taps_rect(ConvSpec* s, int kh, int kw, int pad) {
+  s->ntaps = kh * kw;
+  for (int i = 0; i < kh; ++i)
+    for (int j = 0; j < kw; ++j) { s->dh[i * kw + j] = (int8_t)(i - pad); s->dw[i * kw + j] = (int8_t)(j - pad); }
+}
+
+static unsigned stream_grid(long long work_items, int threads) {
+  const long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;   // 16 x 256-thread CTAs per SM = full occupancy
+  return (unsigned)std::max(1LL, std::min(blocks, cap));
+}
+
+// ------------------------------------------------------------------------------------------
+// single-operator entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int uwm_conv2d_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                    const void* d_wgt, const float* d_bias, int cout, int kh, int kw,
+                                    int stride, int pad, const void* d_res, int res_pitch, int relu,
+                                    void* d_y, int y_pitch, void* stream) {
+  if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d: null pointer");
+  if (cout % 16) return fail(UWM_EINVAL, "conv2d: cout=%d must be a multiple of 16", cout);
+  if (kh * kw > kMaxTaps) return fail(UWM_EINVAL, "conv2d: %dx%d kernel unsupported", kh, kw);
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = cin; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = cout; s.cout_pad = cout;
+  taps_rect(&s, kh, kw, pad);
+  s.stride = stride;
+  s.h_out = (h + 2 * pad - kh) / stride + 1;
+  s.w_out = (w + 2 * pad - kw) / stride + 1;
+  s.res = d_res; s.res_pitch = res_pitch; s.relu = relu;
+  s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_conv(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uwm_head_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                  const void* d_wgt, const float* d_bias, float* d_logits,
+                                  int apply_sigmoid, uint8_t* d_mask, float thr_logit, void* stream) {
+  if (!d_x || !d_wgt || !d_bias) return fail(UWM_EINVAL, "head: null pointer");
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = cin; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = 1; s.cout_pad = 16;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 1; s.h_out = h; s.w_out = w;
+  s.head = 1; s.apply_sigmoid = apply_sigmoid; s.logits = d_logits; s.mask = d_mask; s.thr_logit = thr_logit;
+  ConvLaunch L;
+  int rc = build_conv(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
+static int launch_maxpool(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
+                          cudaStream_t st) {
+  if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
+  const long long items = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool3x3s2_kernel<<<stream_grid(items, 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
+  return post_launch("maxpool3x3s2_kernel", st);
+}
+static int launch_upsample(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
+                           cudaStream_t st) {
+  if (c % 8) return fail(UWM_EINVAL, "upsample: c%%8 must be 0");
+  const long long items = (long long)n * (h * 2) * (w * 2) * (c / 8);
+  upsample2x_kernel<<<stream_grid(items, 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
+  return post_launch("upsample2x_kernel", st);
+}
+static int launch_prep(const void* in, int fmt, int n, int h, int w, void* y, cudaStream_t st) {
+  if (h % 2 || w % 2) return fail(UWM_EINVAL, "prep: h, w must be even");
+  const long long items = (long long)n * (h / 2) * (w / 2);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
+  if (fmt == UWM_IN_U8_NHWC)
+    prep_s2d_kernel<true><<<stream_grid(items, 256), 256, 0, st>>>(in, out, n, h, w);
+  else if (fmt == UWM_IN_F32_NCHW)
+    prep_s2d_kernel<false><<<stream_grid(items, 256), 256, 0, st>>>(in, out, n, h, w);
+  else
+    return fail(UWM_EINVAL, "prep: unknown input format %d", fmt);
+  return post_launch("prep_s2d_kernel", st);
+}
+
+extern "C" int uwm_maxpool3x3s2_nhwc_bf16(const void* d_x, int n, int h, int w, int c, int x_pitch,
+                                          void* d_y, int y_pitch, void* stream) {
+  if (!d_x || !d_y) return fail(UWM_EINVAL, "maxpool: null pointer");
+  return launch_maxpool(d_x, n, h, w, c, x_pitch, d_y, y_pitch, static_cast<cudaStream_t>(stream));
+}
+extern "C" int uwm_upsample2x_nhwc_bf16(const void* d_x, int n, int h, int w, int c, int x_pitch,
+                                        void* d_y, int y_pitch, void* stream) {
+  if (!d_x || !d_y) return fail(UWM_EINVAL, "upsample: null pointer");
+  return launch_upsample(d_x, n, h, w, c, x_pitch, d_y, y_pitch, static_cast<cudaStream_t>(stream));
+}
+extern "C" int uwm_prep_input(const void* d_in, int in_fmt, int n, int h, int w, void* d_y, void* stream) {
+  if (!d_in || !d_y) return fail(UWM_EINVAL, "prep: null pointer");
+  return launch_prep(d_in, in_fmt, n, h, w, d_y, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// model plan
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Buf {
+  size_t bytes_per_img = 0;
+  int first = 1 << 30, last = -1;
+  size_t off_per_img = 0;
+};
+struct TRef {            // a [B,h,w,c] bf16 view: channels [c_off, c_off+c) of a pitch-wide buffer
+  int buf = -1, c_off = 0, c = 0, pitch = 0, h = 0, w = 0;
+};
+enum OpType { OP_PREP, OP_CONV, OP_HEAD, OP_POOL, OP_UP };
+struct Op {
+  OpType type;
+  std::string name;
+  TRef in, out, res;
+  bool has_res = false;
+  int layer = -1;
+  double flops_per_img = 0, bytes_per_img = 0;
+};
+struct Layer {
+  uwm_layer_desc d;
+  bool stem = false;
+  void* d_w = nullptr;
+  float* d_b = nullptr;
+  bool set = false;
+};
+struct Launch {          // one kernel of an instantiated plan
+  OpType type;
+  ConvLaunch conv;       // OP_CONV / OP_HEAD
+  const void* src = nullptr; void* dst = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  long long src_pitch = 0, dst_pitch = 0;
+};
+using GraphKey = std::tuple<int, const void*, int, float*, int, uint8_t*, float>;
+
+}  // namespace
+
+struct uwm_model {
+  int encoder = 34, H = 0, W = 0, max_batch = 0;
+  int dec[5] = {0};
+  bool keep_all = false;
+  std::vector<Buf> bufs;
+  std::vector<Op> ops;
+  std::vector<Layer> layers;
+  std::map<std::string, TRef> named;
+  size_t arena_bytes = 0;
+  uint8_t* arena = nullptr;
+  double flops_per_img = 0;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  cudaStream_t cap_stream = nullptr;
+
+  int new_buf(size_t bytes_per_img) {
+    Buf b; b.bytes_per_img = (bytes_per_img + 1023) & ~(size_t)1023;
+    bufs.push_back(b);
+    return (int)bufs.size() - 1;
+  }
+  TRef dense(int h, int w, int c) {
+    TRef t; t.buf = new_buf((size_t)h * w * c * 2); t.c_off = 0; t.c = c; t.pitch = c; t.h = h; t.w = w;
+    return t;
+  }
+  void* ptr(const TRef& t) const {
+    return arena + bufs[t.buf].off_per_img * (size_t)max_batch + (size_t)t.c_off * 2;
+  }
+  void touch(const TRef& t, int op_idx) {
+    Buf& b = bufs[t.buf];
+    b.first = std::min(b.first, op_idx);
+    b.last = std::max(b.last, op_idx);
+  }
+};
+
+static int add_layer(uwm_model* m, const std::string& conv_key, const std::string& bn_key, int cin,
+                     int cout, int k, int stride, int pad, int relu, int has_res, bool stem = false) {
+  Layer L;
+  memset(&L.d, 0, sizeof(L.d));
+  snprintf(L.d.conv_key, sizeof(L.d.conv_key), "%s", conv_key.c_str());
+  snprintf(L.d.bn_key, sizeof(L.d.bn_key), "%s", bn_key.c_str());
+  L.d.cin = cin; L.d.cout = cout; L.d.cout_pad = (cout + 15) / 16 * 16;
+  L.d.kh = k; L.d.kw = k; L.d.stride = stride; L.d.pad = pad;
+  L.d.relu = relu; L.d.has_residual = has_res;
+  L.stem = stem;
+  if (stem) {
+    L.d.pack = UWM_PACK_STEM_S2D;
+    L.d.w_elems = (int64_t)L.d.cout_pad * 16 * 16;
+  } else {
+    L.d.pack = UWM_PACK_TAPS;
+    L.d.w_elems = (int64_t)L.d.cout_pad * k * k * cin;
+  }
+  L.d.b_elems = L.d.cout_pad;
+  m->layers.push_back(L);
+  return (int)m->layers.size() - 1;
+}
+
+// conv op: output spatial size is derived from the layer's stride/pad
+static void add_conv(uwm_model* m, int layer, const TRef& in, const TRef& out, const TRef* res, bool head = false) {
+  Op op;
+  op.type = head ? OP_HEAD : OP_CONV;
+  const uwm_layer_desc& d = m->layers[layer].d;
+  op.name = d.conv_key;
+  op.in = in; op.out = out; op.layer = layer;
+  if (res) { op.res = *res; op.has_res = true; }
+  const double px = (double)out.h * out.w;
+  op.flops_per_img = 2.0 * d.cin * d.cout * d.kh * d.kw * px;
+  const double in_px = m->layers[layer].stem ? (double)(in.h * 2) * (in.w * 2) : (double)in.h * in.w;
+  op.bytes_per_img = 2.0 * in_px * d.cin + (head ? 5.0 * px : 2.0 * px * d.cout) + (res ? 2.0 * px * d.cout : 0.0);
+  m->layers[layer].d.flops_per_image = op.flops_per_img;
+  m->flops_per_img += op.flops_per_img;
+  m->ops.push_back(op);
+}
+
+static std::string fmt(const char* f, ...) {
+  char b[160];
+  va_list ap; va_start(ap, f); vsnprintf(b, sizeof(b), f, ap); va_end(ap);
+  return b;
+}
+
+static int build_plan(uwm_model* m) {
+  const int H = m->H, W = m->W;
+  const bool r50 = (m->encoder == 50);
+  const int enc_ch[5] = {64, r50 ? 256 : 64, r50 ? 512 : 128, r50 ? 1024 : 256, r50 ? 2048 : 512};
+  const int nblk[4] = {3, 4, 6, 3};
+  const int planes[4] = {64, 128, 256, 512};
+  const int* dec = m->dec;
+  for (int i = 0; i < 5; ++i)
+    if (dec[i] <= 0 || dec[i] % 16)
+      return fail(UWM_EINVAL, "decoder_channels[%d]=%d: must be a positive multiple of 16", i, dec[i]);
+
+  // decoder concat buffers: block i consumes [ up(x_i) (cx ch) | skip (cs ch) ] at 1/2^(4-i) scale
+  const int cx[5] = {enc_ch[4], dec[0], dec[1], dec[2], dec[3]};
+  const int cs[5] = {enc_ch[3], enc_ch[2], enc_ch[1], enc_ch[0], 0};
+  TRef cat[5];
+  for (int i = 0; i < 5; ++i) cat[i] = m->dense(H >> (4 - i), W >> (4 - i), cx[i] + cs[i]);
+  auto skip_slot = [&](int i) {  // where encoder feature feeding decoder block i is written
+    TRef t = cat[i]; t.c_off = cx[i]; t.c = cs[i]; return t;
+  };
+
+  // ---- input prep + stem ----
+  TRef xs = m->dense(H / 2, W / 2, 16);
+  { Op op; op.type = OP_PREP; op.name = "prep"; op.out = xs;
+    op.bytes_per_img = 12.0 * H * W /*fp32 in (u8: 3)*/ + 2.0 * (H / 2) * (W / 2) * 16; m->ops.push_back(op); }
+  TRef f1 = skip_slot(3);   // stem output, 64 ch @ H/2
+  int l = add_layer(m, "encoder.conv1", "encoder.bn1", 3, 64, 7, 2, 3, 1, 0, /*stem=*/true);
+  add_conv(m, l, xs, f1, nullptr);
+  m->named["encoder.stem"] = f1;
+  TRef x = m->dense(H / 4, W / 4, 64);
+  { Op op; op.type = OP_POOL; op.name = "encoder.maxpool"; op.in = f1; op.out = x;
+    op.bytes_per_img = 2.0 * 64 * ((double)(H / 2) * (W / 2) + (double)(H / 4) * (W / 4)); m->ops.push_back(op); }
+  m->named["encoder.maxpool"] = x;
+
+  // ---- residual stages ----
+  int cur_c = 64, cur_h = H / 4, cur_w = W / 4;
+  for (int li = 0; li < 4; ++li) {
+    const int out_c = r50 ? planes[li] * 4 : planes[li];
+    for (int b = 0; b < nblk[li]; ++b) {
+      const int stride = (b == 0 && li > 0) ? 2 : 1;
+      const int oh = cur_h / stride, ow = cur_w / stride;
+      const std::string pre = fmt("encoder.layer%d.%d", li + 1, b);
+      const bool last = (b == nblk[li] - 1);
+      TRef out;
+      if (last && li < 3) out = skip_slot(2 - li);        // layer1->cat[2], layer2->cat[1], layer3->cat[0]
+      else out = m->dense(oh, ow, out_c);
+      out.h = oh; out.w = ow;
+      TRef identity = x;
+      const bool need_ds = (b == 0) && (stride != 1 || cur_c != out_c);
+      if (need_ds) {
+        TRef ds = m->dense(oh, ow, out_c);
+        int ld = add_layer(m, pre + ".downsample.0", pre + ".downsample.1", cur_c, out_c, 1, stride, 0, 0, 0);
+        add_conv(m, ld, x, ds, nullptr);
+        identity = ds;
+      }
+      if (!r50) {
+        TRef t1 = m->dense(oh, ow, planes[li]);
+        int l1 = add_layer(m, pre + ".conv1", pre + ".bn1", cur_c, planes[li], 3, stride, 1, 1, 0);
+        add_conv(m, l1, x, t1, nullptr);
+        int l2 = add_layer(m, pre + ".conv2", pre + ".bn2", planes[li], planes[li], 3, 1, 1, 1, 1);
+        add_conv(m, l2, t1, out, &identity);
+      } else {  // torchvision Bottleneck v1.5: stride on the 3x3
+        TRef t1 = m->dense(cur_h, cur_w, planes[li]);
+        int l1 = add_layer(m, pre + ".conv1", pre + ".bn1", cur_c, planes[li], 1, 1, 0, 1, 0);
+        add_conv(m, l1, x, t1, nullptr);
+        TRef t2 = m->dense(oh, ow, planes[li]);
+        int l2 = add_layer(m, pre + ".conv2", pre + ".bn2", planes[li], planes[li], 3, stride, 1, 1, 0);
+        add_conv(m, l2, t1, t2, nullptr);
+        int l3 = add_layer(m, pre + ".conv3", pre + ".bn3", planes[li], out_c, 1, 1, 0, 1, 1);
+        add_conv(m, l3, t2, out, &identity);
+      }
+      x = out; cur_c = out_c; cur_h = oh; cur_w = ow;
+    }
+    m->named[fmt("encoder.layer%d", li + 1)] = x;
+  }
+
+  // ---- decoder ----
+  for (int i = 0; i < 5; ++i) {
+    TRef up = cat[i]; up.c_off = 0; up.c = cx[i];
+    { Op op; op.type = OP_UP; op.name = fmt("decoder.blocks.%d.upsample", i); op.in = x; op.out = up;
+      op.bytes_per_img = 2.0 * cx[i] * ((double)x.h * x.w + (double)up.h * up.w); m->ops.push_back(op); }
+    const std::string pre = fmt("decoder.blocks.%d", i);
+    TRef t1 = m->dense(cat[i].h, cat[i].w, dec[i]);
+    int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0);
+    add_conv(m, l1, cat[i], t1, nullptr);
+    TRef t2 = m->dense(cat[i].h, cat[i].w, dec[i]);
+    int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0);
+    add_conv(m, l2, t1, t2, nullptr);
+    x = t2;
+    m->named[pre] = x;
+  }
+  // ---- head ----
+  int lh = add_layer(m, "segmentation_head.0", "", dec[4], 1, 3, 1, 1, 0, 0);
+  TRef none;
+  add_conv(m, lh, x, none, nullptr, /*head=*/true);
+
+  // ---- liveness + arena offsets ----
+  for (int i = 0; i < (int)m->ops.size(); ++i) {
+    Op& op = m->ops[i];
+    if (op.in.buf >= 0) m->touch(op.in, i);
+    if (op.out.buf >= 0) m->touch(op.out, i);
+    if (op.has_res) m->touch(op.res, i);
+  }
+  std::vector<int> order;
+  for (int i = 0; i < (int)m->bufs.size(); ++i) if (m->bufs[i].last >= 0) order.push_back(i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return m->bufs[a].first < m->bufs[b].first; });
+  std::vector<int> placed;
+  size_t top = 0;
+  for (int id : order) {
+    Buf& b = m->bufs[id];
+    size_t off = 0;
+    if (m->keep_all) { off = top; }
+    else {
+      // first-fit among buffers whose lifetime overlaps
+      std::vector<std::pair<size_t, size_t>> busy;
+      for (int pid : placed) {
+        const Buf& pb = m->bufs[pid];
+        if (pb.last >= b.first && pb.first <= b.last) busy.push_back({pb.off_per_img, pb.off_per_img + pb.bytes_per_img});
+      }
+      std::sort(busy.begin(), busy.end());
+      for (auto& iv : busy) {
+        if (off + b.bytes_per_img <= iv.first) break;
+        off = std::max(off, iv.second);
+      }
+    }
+    b.off_per_img = off;
+    top = std::max(top, off + b.bytes_per_img);
+    placed.push_back(id);
+  }
+  m->arena_bytes = top * (size_t)m->max_batch;
+  return UWM_OK;
+}
+
+extern "C" int uwm_model_create(int encoder, const int* decoder_channels, int h, int w, int max_batch,
+                                uwm_model** out) {
+  if (!out || !decoder_channels) return fail(UWM_EINVAL, "model_create: null pointer");
+  if (encoder != 34 && encoder != 50) return fail(UWM_EINVAL, "model_create: encoder resnet%d unsupported (34|50)", encoder);
+  if (h <= 0 || w <= 0 || h % 32 || w % 32)
+    return fail(UWM_EINVAL, "Wrong input shape height=%d, width=%d. Expected image height and width divisible by 32.", h, w);
+  if (max_batch < 1) return fail(UWM_EINVAL, "model_create: max_batch must be >= 1");
+  uwm_model* m = new uwm_model();
+  m->encoder = encoder; m->H = h; m->W = w; m->max_batch = max_batch;
+  for (int i = 0; i < 5; ++i) m->dec[i] = decoder_channels[i];
+  const char* ka = getenv("UWM_KEEP_ALL");
+  m->keep_all = ka && ka[0] == '1';
+  int rc = build_plan(m);
+  if (rc) { delete m; return rc; }
+  cudaError_t e = cudaMalloc(&m->arena, m->arena_bytes);
+  if (e != cudaSuccess) {
+    rc = fail(UWM_ENOMEM, "cudaMalloc(%zu bytes of activation workspace) failed: %s", m->arena_bytes, cudaGetErrorString(e));
+    delete m; return rc;
+  }
+  e = cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { rc = fail(UWM_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); cudaFree(m->arena); delete m; return rc; }
+  *out = m;
+  return UWM_OK;
+}
+
+extern "C" int uwm_model_destroy(uwm_model* m) {
+  if (!m) return UWM_OK;
+  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& L : m->layers) { if (L.d_w) cudaFree(L.d_w); if (L.d_b) cudaFree(L.d_b); }
+  if (m->arena) cudaFree(m->arena);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  delete m;
+  return UWM_OK;
+}
+extern "C" int uwm_model_num_layers(const uwm_model* m) { return m ? (int)m->layers.size() : 0; }
+extern "C" int uwm_model_layer_desc(const uwm_model* m, int i, uwm_layer_desc* d) {
+  if (!m || !d || i < 0 || i >= (int)m->layers.size()) return fail(UWM_EINVAL, "layer_desc: bad index %d", i);
+  *d = m->layers[i].d;
+  return UWM_OK;
+}
+extern "C" int uwm_model_set_layer(uwm_model* m, int i, const void* wgt, int64_t w_elems, const float* bias,
+                                   int64_t b_elems) {
+  if (!m || !wgt || !bias || i < 0 || i >= (int)m->layers.size()) return fail(UWM_EINVAL, "set_layer: bad argument");
+  Layer& L = m->layers[i];
+  if (w_elems != L.d.w_elems || b_elems != L.d.b_elems)
+    return fail(UWM_EINVAL, "set_layer(%s): expected %lld weight / %lld bias elements, got %lld / %lld", L.d.conv_key,
+                (long long)L.d.w_elems, (long long)L.d.b_elems, (long long)w_elems, (long long)b_elems);
+  if (!L.d_w) CUDA_TRY(cudaMalloc(&L.d_w, (size_t)w_elems * 2));
+  if (!L.d_b) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&L.d_b), (size_t)b_elems * 4));
+  CUDA_TRY(cudaMemcpy(L.d_w, wgt, (size_t)w_elems * 2, cudaMemcpyDefault));
+  CUDA_TRY(cudaMemcpy(L.d_b, bias, (size_t)b_elems * 4, cudaMemcpyDefault));
+  L.set = true;
+  return UWM_OK;
+}
+extern "C" size_t uwm_model_workspace_bytes(const uwm_model* m) { return m ? m->arena_bytes : 0; }
+extern "C" int uwm_model_num_kernels(const uwm_model* m) { return m ? (int)m->ops.size() : 0; }
+extern "C" double uwm_model_flops_per_image(const uwm_model* m) { return m ? m->flops_per_img : 0.0; }
+
+// Instantiate the launches of one forward for `batch` images.
+static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, float* d_logits, int apply_sigmoid,
+                       uint8_t* d_mask, float thr_logit, std::vector<Launch>* out) {
+  out->clear();
+  out->reserve(m->ops.size());
+  for (const Op& op : m->ops) {
+    Launch L;
+    L.type = op.type;
+    switch (op.type) {
+      case OP_PREP:
+        L.src = d_in; L.dst = m->ptr(op.out); L.n = batch; L.h = m->H; L.w = m->W; L.c = in_fmt;
+        break;
+      case OP_POOL:
+      case OP_UP:
+        L.src = m->ptr(op.in); L.dst = m->ptr(op.out); L.n = batch; L.h = op.in.h; L.w = op.in.w; L.c = op.in.c;
+        L.src_pitch = op.in.pitch; L.dst_pitch = op.out.pitch;
+        break;
+      case OP_CONV:
+      case OP_HEAD: {
+        const Layer& ly = m->layers[op.layer];
+        if (!ly.set) return fail(UWM_ESTATE, "weights of layer %s not set", ly.d.conv_key);
+        ConvSpec s;
+        s.x = m->ptr(op.in); s.n = batch; s.h = op.in.h; s.w = op.in.w; s.x_pitch = op.in.pitch;
+        s.wgt = ly.d_w; s.bias = ly.d_b; s.cout = ly.d.cout; s.cout_pad = ly.d.cout_pad;
+        if (ly.stem) {
+          s.cin = 16; s.stride = 1;
+          s.ntaps = 16;
+          for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { s.dh[r * 4 + c] = (int8_t)(r - 2); s.dw[r * 4 + c] = (int8_t)(c - 2); }
+          s.h_out = op.in.h; s.w_out = op.in.w;
+        } else {
+          s.cin = ly.d.cin; s.stride = ly.d.stride;
+          taps_rect(&s, ly.d.kh, ly.d.kw, ly.d.pad);
+          s.h_out = (op.in.h + 2 * ly.d.pad - ly.d.kh) / ly.d.stride + 1;
+          s.w_out = (op.in.w + 2 * ly.d.pad - ly.d.kw) / ly.d.stride + 1;
+        }
+        s.relu = ly.d.relu;
+        if (op.type == OP_HEAD) {
+          s.head = 1; s.apply_sigmoid = apply_sigmoid; s.logits = d_logits; s.mask = d_mask; s.thr_logit = thr_logit;
+        } else {
+          if (s.h_out != op.out.h || s.w_out != op.out.w)
+            return fail(UWM_ESTATE, "plan bug: %s output %dx%d != planned %dx%d", ly.d.conv_key, s.h_out, s.w_out, op.out.h, op.out.w);
+          s.out = m->ptr(op.out); s.out_pitch = op.out.pitch;
+          if (op.has_res) { s.res = m->ptr(op.res); s.res_pitch = op.res.pitch; }
+        }
+        int rc = build_conv(s, &L.conv);
+        if (rc) return rc;
+        break;
+      }
+    }
+    out->push_back(L);
+  }
+  return UWM_OK;
+}
+
+static int run_launch(const Launch& L, cudaStream_t st) {
+  switch (L.type) {
+    case OP_PREP: return launch_prep(L.src, L.c, L.n, L.h, L.w, L.dst, st);
+    case OP_POOL: return launch_maxpool(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
+    case OP_UP: return launch_upsample(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
+    case OP_CONV:
+    case OP_HEAD: return launch_conv(L.conv, st);
+  }
+  return UWM_OK;
+}
+
+static int check_forward_args(uwm_model* m, const void* d_in, int in_fmt, int batch, float* d_logits, uint8_t* d_mask) {
+  if (!m || !d_in) return fail(UWM_EINVAL, "forward: null model/input");
+  if (batch < 1 || batch > m->max_batch) return fail(UWM_ESTATE, "forward: batch %d outside [1, max_batch=%d]", batch, m->max_batch);
+  if (in_fmt != UWM_IN_F32_NCHW && in_fmt != UWM_IN_U8_NHWC) return fail(UWM_EINVAL, "forward: unknown input format %d", in_fmt);
+  if (!d_logits && !d_mask) return fail(UWM_EINVAL, "forward: both outputs are NULL");
+  return UWM_OK;
+}
+
+extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int batch, float* d_logits,
+                                 int apply_sigmoid, uint8_t* d_mask, float thr_logit, int use_graph, void* stream) {
+  int rc = check_forward_args(m, d_in, in_fmt, batch, d_logits, d_mask);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!use_graph || debug_sync()) {
+    std::vector<Launch> ls;
+    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &ls);
+    if (rc) return rc;
+    for (const Launch& L : ls) { rc = run_launch(L, st); if (rc) return rc; }
+    return UWM_OK;
+  }
+  GraphKey key(batch, d_in, in_fmt * 2 + (apply_sigmoid ? 1 : 0), d_logits, 0, d_mask, thr_logit);
+  auto it = m->graphs.find(key);
+  if (it == m->graphs.end()) {
+    std::vector<Launch> ls;
+    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &ls);
+    if (rc) return rc;
+    // make sure function attributes are set outside capture
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed));
+    for (const Launch& L : ls) {
+      rc = run_launch(L, m->cap_stream);
+      if (rc) { cudaStreamEndCapture(m->cap_stream, &g); if (g) cudaGraphDestroy(g); return rc; }
+    }
+    CUDA_TRY(cudaStreamEndCapture(m->cap_stream, &g));
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(UWM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    if (m->graphs.size() >= 16) {   // bound the cache
+      for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+      m->graphs.clear();
+    }
+    it = m->graphs.emplace(key, ex).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second, st));
+  g_launches.fetch_add(m->ops.size(), std::memory_order_relaxed);
+  return UWM_OK;
+}
+
+__global__ void gather_pitched_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      long long pixels, int c, long long pitch) {
+  const int cg = c >> 3;
+  const long long total = pixels * cg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long px = idx / cg; const int g = (int)(idx % cg);
+    *reinterpret_cast<uint4*>(dst + px * c + g * 8) = *reinterpret_cast<const uint4*>(src + px * pitch + g * 8);
+  }
+}
+
+extern "C" int uwm_model_read_tensor(uwm_model* m, const char* name, int batch, void* d_dst, int64_t dst_bytes,
+                                     int* h, int* w, int* c, void* stream) {
+  if (!m || !name) return fail(UWM_EINVAL, "read_tensor: null argument");
+  auto it = m->named.find(name);
+  if (it == m->named.end()) return fail(UWM_EINVAL, "read_tensor: unknown tensor '%s'", name);
+  const TRef& t = it->second;
+  if (h) *h = t.h; if (w) *w = t.w; if (c) *c = t.c;
+  if (!d_dst) return UWM_OK;
+  const long long px = (long long)batch * t.h * t.w;
+  if (dst_bytes < px * t.c * 2) return fail(UWM_EINVAL, "read_tensor: destination too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gather_pitched_kernel<<<stream_grid(px * (t.c / 8), 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(m->ptr(t)), static_cast<__nv_bfloat16*>(d_dst), px, t.c, t.pitch);
+  return post_launch("gather_pitched_kernel", st);
+}
+
+extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int batch, float* d_logits,
+                                 uint8_t* d_mask, float thr_logit, char* names, float* ms, double* flops,
+                                 double* bytes, int n_max, void* stream) {
+  int rc = check_forward_args(m, d_in, in_fmt, batch, d_logits, d_mask);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<Launch> ls;
+  rc = instantiate(m, d_in, in_fmt, batch, d_logits, 0, d_mask, thr_logit, &ls);
+  if (rc) return rc;
+  const int n = (int)ls.size();
+  if (n > n_max) return fail(UWM_EINVAL, "profile: need room for %d kernels", n);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < n; ++i) {
+    rc = run_launch(ls[i], st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev[i + 1], st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    snprintf(names + (size_t)i * 64, 64, "%s", m->ops[i].name.c_str());
+    if (flops) flops[i] = m->ops[i].flops_per_img * batch;
+    if (bytes) bytes[i] = m->ops[i].bytes_per_img * batch;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return n;
+}

@@ -1,0 +1,123 @@
+"""Single-operator wrappers over the C ABI (torch tensors in, torch tensors out).
+
+torch is used only to own device memory and the stream; all arithmetic happens in
+libuwm_b200.so.  Activations are NHWC bf16 (``[N,H,W,C]`` contiguous, or a channel slice of a
+wider buffer described by its pixel pitch).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("unet_watermark_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pitch(t: torch.Tensor) -> int:
+    """pixel pitch of an NHWC view whose channel dim may be a slice of a wider buffer"""
+    assert t.dim() == 4 and t.stride(3) == 1, "expected NHWC with unit channel stride"
+    p = t.stride(2)
+    assert t.stride(1) == p * t.shape[2] and t.stride(0) == p * t.shape[2] * t.shape[1], \
+        "NHWC view must be dense in N,H,W"
+    return p
+
+
+def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, kh: int, kw: int, stride: int,
+           pad: int, relu: bool = False, residual: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NHWC bf16 conv (+bias)(+residual)(+ReLU).  w_packed: [Cout, kh*kw*Cin] bf16 (packing.pack_taps)."""
+    _require_cuda(x, w_packed, bias, residual, out)
+    lib = _lib.load()
+    n, h, w, cin = x.shape
+    cout = w_packed.shape[0]
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_nhwc_bf16(
+        x.data_ptr(), n, h, w, cin, _pitch(x), w_packed.data_ptr(), bias.data_ptr(), cout, kh, kw, stride, pad,
+        residual.data_ptr() if residual is not None else None,
+        _pitch(residual) if residual is not None else 0, int(relu), out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_nhwc_bf16")
+    return out
+
+
+def head(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, threshold: Optional[float] = 0.5,
+         thr_on_logits: bool = False, want_logits: bool = True, apply_sigmoid: bool = False):
+    """conv3x3(Cin->1)+bias -> (fp32 logits [N,H,W] or None, uint8 mask [N,H,W] or None)."""
+    _require_cuda(x, w_packed, bias)
+    lib = _lib.load()
+    n, h, w, cin = x.shape
+    logits = torch.empty(n, h, w, dtype=torch.float32, device=x.device) if want_logits else None
+    mask = torch.empty(n, h, w, dtype=torch.uint8, device=x.device) if threshold is not None else None
+    thr_logit = 0.0
+    if threshold is not None:
+        thr_logit = float(threshold) if thr_on_logits else logit(threshold)
+    rc = lib.uwm_head_nhwc_bf16(x.data_ptr(), n, h, w, cin, _pitch(x), w_packed.data_ptr(), bias.data_ptr(),
+                                logits.data_ptr() if logits is not None else None, int(apply_sigmoid),
+                                mask.data_ptr() if mask is not None else None, thr_logit, _stream())
+    _lib.check(rc, "uwm_head_nhwc_bf16")
+    return logits, mask
+
+
+def logit(p: float) -> float:
+    """threshold on sigmoid(z) > p  <=>  z > log(p/(1-p))"""
+    if p <= 0.0:
+        return -math.inf
+    if p >= 1.0:
+        return math.inf
+    return math.log(p / (1.0 - p))
+
+
+def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, out)
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.uwm_maxpool3x3s2_nhwc_bf16(x.data_ptr(), n, h, w, c, _pitch(x), out.data_ptr(), _pitch(out),
+                                              _stream()), "uwm_maxpool3x3s2_nhwc_bf16")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nearest 2x; `out` may be the leading channel slice of a concat buffer"""
+    _require_cuda(x, out)
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.uwm_upsample2x_nhwc_bf16(x.data_ptr(), n, h, w, c, _pitch(x), out.data_ptr(), _pitch(out),
+                                            _stream()), "uwm_upsample2x_nhwc_bf16")
+    return out
+
+
+def prep_input(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW (normalised) or uint8 NHWC RGB -> bf16 [N,H/2,W/2,16] space-to-depth stem input"""
+    _require_cuda(x)
+    lib = _lib.load()
+    if x.dtype == torch.uint8:
+        n, h, w, c = x.shape
+        fmt = _lib.IN_U8_NHWC
+    elif x.dtype == torch.float32:
+        n, c, h, w = x.shape
+        fmt = _lib.IN_F32_NCHW
+    else:
+        raise TypeError(f"prep_input: unsupported dtype {x.dtype}")
+    if c != 3:
+        raise ValueError("prep_input expects 3 channels")
+    x = x.contiguous()
+    out = torch.empty(n, h // 2, w // 2, 16, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.uwm_prep_input(x.data_ptr(), fmt, n, h, w, out.data_ptr(), _stream()), "uwm_prep_input")
+    return out
