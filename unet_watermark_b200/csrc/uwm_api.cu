@@ -374,7 +374,10 @@ struct Launch {          // one kernel of an instantiated plan
   int n = 0, h = 0, w = 0, c = 0;
   long long src_pitch = 0, dst_pitch = 0;
 };
-using GraphKey = std::tuple<int, const void*, int, float*, int, uint8_t*, float>;
+struct Plan {            // launches of one forward at a fixed batch size (+ the captured body graph)
+  std::vector<Launch> launches;
+  cudaGraphExec_t body = nullptr;
+};
 
 }  // namespace
 
@@ -389,7 +392,7 @@ struct uwm_model {
   size_t arena_bytes = 0;
   uint8_t* arena = nullptr;
   double flops_per_img = 0;
-  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<int, Plan> plans;
   cudaStream_t cap_stream = nullptr;
 
   int new_buf(size_t bytes_per_img) {
@@ -615,7 +618,7 @@ extern "C" int uwm_model_create(int encoder, const int* decoder_channels, int h,
 
 extern "C" int uwm_model_destroy(uwm_model* m) {
   if (!m) return UWM_OK;
-  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : m->plans) if (kv.second.body) cudaGraphExecDestroy(kv.second.body);
   for (auto& L : m->layers) { if (L.d_w) cudaFree(L.d_w); if (L.d_b) cudaFree(L.d_b); }
   if (m->arena) cudaFree(m->arena);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
@@ -724,41 +727,46 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
   int rc = check_forward_args(m, d_in, in_fmt, batch, d_logits, d_mask);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!use_graph || debug_sync()) {
-    std::vector<Launch> ls;
-    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &ls);
+  auto pit = m->plans.find(batch);
+  if (pit == m->plans.end()) {
+    // tensor maps and tile shapes depend on the batch only; pointers of the first (prep) and last
+    // (head) kernels are patched per call, so the cached plan and its graph are reusable.
+    Plan pl;
+    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &pl.launches);
     if (rc) return rc;
-    for (const Launch& L : ls) { rc = run_launch(L, st); if (rc) return rc; }
+    pit = m->plans.emplace(batch, std::move(pl)).first;
+  }
+  Plan& pl = pit->second;
+  Launch& first = pl.launches.front();
+  Launch& last = pl.launches.back();
+  first.src = d_in; first.c = in_fmt;
+  last.conv.args.logits = d_logits; last.conv.args.mask = d_mask;
+  last.conv.args.thr_logit = thr_logit; last.conv.args.apply_sigmoid = apply_sigmoid;
+  const size_t n = pl.launches.size();
+  if (!use_graph || debug_sync() || n < 3) {
+    for (const Launch& L : pl.launches) { rc = run_launch(L, st); if (rc) return rc; }
     return UWM_OK;
   }
-  GraphKey key(batch, d_in, in_fmt * 2 + (apply_sigmoid ? 1 : 0), d_logits, 0, d_mask, thr_logit);
-  auto it = m->graphs.find(key);
-  if (it == m->graphs.end()) {
-    std::vector<Launch> ls;
-    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &ls);
-    if (rc) return rc;
-    // make sure function attributes are set outside capture
+  if (!pl.body) {
+    // capture everything between prep and head (all pointers library-owned) once per batch size
     CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cudaGraph_t g = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed));
-    for (const Launch& L : ls) {
-      rc = run_launch(L, m->cap_stream);
+    for (size_t i = 1; i + 1 < n; ++i) {
+      rc = run_launch(pl.launches[i], m->cap_stream);
       if (rc) { cudaStreamEndCapture(m->cap_stream, &g); if (g) cudaGraphDestroy(g); return rc; }
     }
     CUDA_TRY(cudaStreamEndCapture(m->cap_stream, &g));
-    cudaGraphExec_t ex = nullptr;
-    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaError_t e = cudaGraphInstantiate(&pl.body, g, 0);
     cudaGraphDestroy(g);
-    if (e != cudaSuccess) return fail(UWM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-    if (m->graphs.size() >= 16) {   // bound the cache
-      for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
-      m->graphs.clear();
-    }
-    it = m->graphs.emplace(key, ex).first;
+    if (e != cudaSuccess) { pl.body = nullptr; return fail(UWM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    g_launches.fetch_sub(n - 2, std::memory_order_relaxed);   // capture is not execution
   }
-  CUDA_TRY(cudaGraphLaunch(it->second, st));
-  g_launches.fetch_add(m->ops.size(), std::memory_order_relaxed);
-  return UWM_OK;
+  rc = run_launch(first, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaGraphLaunch(pl.body, st));
+  g_launches.fetch_add(n - 2, std::memory_order_relaxed);
+  return run_launch(last, st);
 }
 
 __global__ void gather_pitched_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
