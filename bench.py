@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""Benchmark of the UNet watermark-mask inference hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" = one forward of smp-Unet-resnet34 over one batch of 16 synthetic 512x512 RGB images per GPU
+(BASELINE.json configs[1]) ending in the fused sigmoid+threshold uint8 mask.  Data-parallel, weak
+scaling, no collective on the data path.  Prints ONE JSON line on rank 0.
+
+  value     images/s, whole job, inputs already resident in HBM (uint8 NHWC), CUDA-event timed
+  e2e       images/s through the public API (Unet.predict_mask) from pinned HOST uint8 batches:
+            H2D copy + forward + D2H read of the uint8 masks inside the timed region
+  roofline  conv_tc_kernel (the tcgen05 implicit-GEMM kernel, all conv launches of a step):
+            algorithmic conv FLOPs / summed per-launch CUDA-event time, vs the measured bf16 peak
+  cpu_baseline / --impl reference
+            the oracle restatement of the reference's CPU path (torch fp32, all host threads) on a
+            bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec UNet-ResNet34 512x512 bf16 mask inference"
+UNIT = "images/s"
+ENCODER, SIZE, BATCH = "resnet34", 512, 16
+WORKLOAD = "configs[1]: smp Unet resnet34, 512x512, batch 16 per GPU, bf16 inference, sigmoid+threshold uint8 mask"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": float(d["bf16_tflops"]), "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", 0)),
+                "hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, ~5 ms period)."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(steps: int, warmup: int, images_per_step: int):
+    """The reference's CPU path (oracle restatement, torch fp32, all host threads): img/s."""
+    import torch
+    from oracle import unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build(ENCODER, seed=0, random_bn=True)
+    x = O.image_like_input(images_per_step, SIZE, seed=1)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.binarize(model(x)[:, 0])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.binarize(model(x)[:, 0])
+        dt = time.perf_counter() - t0
+    return images_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = 2
+    v, ms, cores = cpu_reference_run(args.steps, max(args.warmup, 1), per_step)
+    sample = f"{per_step} of {BATCH} images per step, fp32, oracle port of the reference CPU path, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from unet_watermark_b200 import _lib
+    from unet_watermark_b200.unet_model import Unet
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    lib = _lib.load()
+
+    # random-init weights of the named architecture (no checkpoints offline), non-trivial BN statistics
+    torch.manual_seed(0)
+    model = Unet(ENCODER, encoder_weights=None)
+    g = torch.Generator().manual_seed(1)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.8, 1.2, generator=g)
+            m.bias.data.normal_(0, 0.1, generator=g)
+            m.running_mean.normal_(0, 0.1, generator=g)
+            m.running_var.uniform_(0.7, 1.3, generator=g)
+    model = model.to(dev).eval()
+
+    # synthetic uint8 RGB batches; the rotating pool (12.6 MB each) is larger than the 126 MB L2
+    n_pool = 12
+    gi = torch.Generator().manual_seed(100 + rank)
+    host_pool = [torch.randint(0, 256, (BATCH, SIZE, SIZE, 3), dtype=torch.uint8, generator=gi).pin_memory()
+                 for _ in range(n_pool)]
+    dev_pool = [h.to(dev) for h in host_pool]
+    eng = model.engine(BATCH, SIZE, SIZE, dev)
+    flops_step = eng.flops_per_image * BATCH
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        model.predict_mask(dev_pool[i % n_pool], 0.5)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.uwm_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        mask = model.predict_mask(dev_pool[i % n_pool], 0.5)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = int(lib.uwm_kernel_launch_count() - l0)
+    ms_total = e0.elapsed_time(e1)
+    checksum = int(mask.sum().item())
+
+    # ---- end to end through the public API with host buffers ---------------------------------
+    out_host = torch.empty(BATCH, SIZE, SIZE, dtype=torch.uint8).pin_memory()
+    for i in range(3):
+        out_host.copy_(model.predict_mask(host_pool[i % n_pool].to(dev, non_blocking=True), 0.5))
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        x = host_pool[i % n_pool].to(dev, non_blocking=True)           # H2D of this step's inputs
+        out_host.copy_(model.predict_mask(x, 0.5), non_blocking=True)   # D2H of this step's masks
+        torch.cuda.current_stream().synchronize()                      # the caller consumes the masks
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel (conv_tc_kernel) -----------------------------------
+    conv_ms = conv_flops = other_ms = 0.0
+    reps = 5
+    per_kernel = {}
+    for r in range(reps + 1):
+        prof = eng.profile(dev_pool[r % n_pool], 0.5)
+        if r == 0:
+            continue                                   # warm-up pass
+        for name, ms, fl, by in prof:
+            if fl > 0:
+                conv_ms += ms
+                conv_flops += fl
+            else:
+                other_ms += ms
+            a = per_kernel.setdefault(name, [0.0, fl, by])
+            a[0] += ms / reps
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get("conv_tc_kernel_dram_bytes_per_step")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                "peak_source": peaks["source"] + ", burst figure",
+                "how": f"sum of algorithmic conv FLOPs of one step ({flops_step / 1e12:.4f} TFLOP) / summed CUDA-event "
+                       f"time of its {sum(1 for v in per_kernel.values() if v[1] > 0)} conv_tc_kernel launches, "
+                       f"eager pass, mean of {reps}",
+                "conv_ms_per_step": conv_ms / reps, "glue_ms_per_step": other_ms / reps,
+                "hbm_peak_gbs": peaks["hbm_gbs"]}
+
+    if rank == 0:
+        value = world * BATCH * args.steps / (ms_total * 1e-3)
+        e2e_v = world * BATCH * args.steps / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "encoder": ENCODER, "image": [SIZE, SIZE], "batch_per_gpu": BATCH,
+                           "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                           "weights": "random-init (seeded), BatchNorm folded",
+                           "l2": f"inputs rotate through {n_pool} batches ({n_pool * BATCH * SIZE * SIZE * 3 / 1e6:.0f} MB) > 126 MB L2; "
+                                 f"per-step activation traffic also exceeds L2",
+                           "cuda_graph": True},
+                "tflops": value * eng.flops_per_image / 1e12,
+                "frac_of_bf16_peak": value * eng.flops_per_image / 1e12 / world / peaks["bf16_tflops"],
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": BATCH * SIZE * SIZE * 3,
+                        "d2h_bytes_per_step": BATCH * SIZE * SIZE, "ms_per_step": ms_e2e / args.steps,
+                        "api": "Unet.predict_mask(pinned host uint8 NHWC -> cuda) -> uint8 masks -> pinned host"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "mask_checksum": checksum}
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference_run(steps=5, warmup=1, images_per_step=2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "5 timed steps x 2 images (of the 16-image batch), fp32, oracle port of "
+                                              "the reference CPU path, all host threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,181 @@
+"""End-to-end parity of the B200 path against the oracle (through the reference-shaped Python seam, which
+calls the C ABI).
+
+Tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle), stated relative to
+the logit scale of the fixture:
+    max |d|  <= 8 % of max|logit|         mean |d| <= 5 % of std(logit)
+and against the bf16-emulating oracle (same quantisation points, so only fp32 summation order differs)
+the early, un-amplified tensors must agree to a bf16 ulp.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from unet_watermark_b200 import _lib
+from unet_watermark_b200.config import get_cfg_defaults
+from unet_watermark_b200.unet_model import Unet, create_model_from_config
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+MAX_FRAC, MEAN_FRAC = 0.08, 0.05
+
+
+def make_pair(enc, dev, seed=0, random_bn=True, dec=(256, 128, 64, 32, 16), activation=None):
+    ref = O.build(enc, decoder_channels=dec, seed=seed, random_bn=random_bn, activation=activation)
+    m = Unet(enc, encoder_weights=None, decoder_channels=dec, activation=activation)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    return ref, m.to(dev).eval()
+
+
+def assert_close_to_oracle(y, y32):
+    d = (y - y32).abs()
+    assert d.max() <= MAX_FRAC * y32.abs().max(), (d.max().item(), y32.abs().max().item())
+    assert d.mean() <= MEAN_FRAC * y32.std(), (d.mean().item(), y32.std().item())
+
+
+@pytest.mark.parametrize("enc,size,batch", [("resnet34", (128, 128), 2), ("resnet34", (96, 160), 3),
+                                            ("resnet34", (32, 32), 1), ("resnet50", (96, 96), 2)])
+def test_logits_match_oracle(enc, size, batch, cuda_device):
+    ref, m = make_pair(enc, cuda_device)
+    x = O.image_like_input(batch, size, seed=3)
+    with torch.no_grad():
+        y32 = ref(x)
+    before = _lib.load().uwm_kernel_launch_count()
+    y = m(x.to(cuda_device))
+    assert _lib.load().uwm_kernel_launch_count() - before == m.engine(batch, *size).kernels_per_forward
+    assert y.shape == y32.shape and y.dtype == torch.float32 and y.is_cuda
+    assert_close_to_oracle(y.cpu(), y32)
+    # and at least as close as stock bf16 emulation of the same network is to fp32
+    yemu = O.forward_bf16_emulated(ref, x)
+    assert (y.cpu() - y32).abs().mean() <= 1.5 * (yemu - y32).abs().mean() + 1e-3
+
+
+def test_early_features_match_bf16_emulation_to_one_ulp(cuda_device, monkeypatch):
+    monkeypatch.setenv("UWM_KEEP_ALL", "1")           # keep every intermediate buffer alive
+    ref, m = make_pair("resnet34", cuda_device, seed=2)
+    x = O.image_like_input(2, 64, seed=9)
+    _, feats = O.forward_bf16_emulated(ref, x, return_features=True)
+    m(x.to(cuda_device))
+    eng = m.engine(2, 64, 64)
+    for name, ulps in (("encoder.stem", 1), ("encoder.maxpool", 1), ("encoder.layer1", 8)):
+        t = eng.read_tensor(name, 2).float().cpu().permute(0, 3, 1, 2)
+        f = feats[name]
+        tol = ulps * 2.0 ** -8 * f.abs().clamp_min(2.0 ** -6)
+        frac_off = ((t - f).abs() > tol).float().mean().item()
+        assert frac_off < 1e-3, (name, frac_off)
+    for name in ("encoder.layer4", "decoder.blocks.0", "decoder.blocks.4"):
+        t = eng.read_tensor(name, 2).float().cpu().permute(0, 3, 1, 2)
+        assert (t - feats[name]).abs().mean() <= 0.02 * feats[name].std(), name
+
+
+@pytest.mark.parametrize("enc", ["resnet34", "resnet50"])
+def test_against_committed_golden_vectors(enc, cuda_device):
+    g = np.load(os.path.join(GOLD, f"unet_{enc}_64.npz"))
+    ref, m = make_pair(enc, cuda_device, seed=int(g["model_seed"]))
+    x = O.image_like_input(int(g["batch"]), int(g["size"]), seed=int(g["input_seed"]))
+    y = m(x.to(cuda_device)).cpu()
+    assert_close_to_oracle(y, torch.from_numpy(g["logits_fp32"]))
+
+
+def test_graph_eager_identical_and_deterministic(cuda_device):
+    ref, m = make_pair("resnet34", cuda_device)
+    x = O.image_like_input(3, 64, seed=1).to(cuda_device)
+    m.use_cuda_graph = False
+    y0 = m(x).clone()
+    m.use_cuda_graph = True
+    y1, y2 = m(x).clone(), m(x).clone()
+    assert torch.equal(y0, y1) and torch.equal(y1, y2)
+    # smaller batch on the same engine (plan cache per batch size)
+    assert torch.equal(m(x[:2]), y0[:2])
+
+
+def test_u8_fast_path_equals_normalised_f32_path(cuda_device):
+    ref, m = make_pair("resnet34", cuda_device)
+    u8 = O.image_like_u8(2, 64, seed=4)
+    mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+    xn = (u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    mask, lu = m.predict_mask(u8.to(cuda_device), 0.5, return_logits=True)
+    lf = m(xn.to(cuda_device))
+    assert (lu - lf).abs().max() <= 0.02 * lf.abs().max()
+    with torch.no_grad():
+        assert_close_to_oracle(lu.cpu(), ref(xn))
+
+
+def test_mask_conventions_and_sigmoid_activation(cuda_device):
+    ref, m = make_pair("resnet34", cuda_device)
+    x = O.image_like_input(2, 64, seed=6).to(cuda_device)
+    y = m(x)
+    assert torch.equal(m.predict_mask(x, 0.5, sigmoid=True), (y[:, 0] > 0).to(torch.uint8) * 255)
+    assert torch.equal(m.predict_mask(x, 0.5, sigmoid=False), (y[:, 0] > 0.5).to(torch.uint8) * 255)
+    assert torch.equal(m.predict_mask(x, 0.3, sigmoid=True), (y[:, 0] > float(np.log(0.3 / 0.7))).to(torch.uint8) * 255)
+    p = m.predict_proba(x)
+    assert (p - torch.sigmoid(y)).abs().max() < 1e-5
+    refs, ms = make_pair("resnet34", cuda_device, activation="sigmoid")
+    ps = ms(x)
+    assert (ps - torch.sigmoid(y)).abs().max() < 1e-5             # same weights (seed), sigmoid head
+    assert torch.equal(ms.predict_mask(x, 0.5), (y[:, 0] > 0).to(torch.uint8) * 255)
+
+
+def test_errors_match_reference_contract(cuda_device):
+    _, m = make_pair("resnet34", cuda_device)
+    with pytest.raises(RuntimeError, match="divisible by 32"):
+        m(torch.zeros(1, 3, 100, 64, device=cuda_device))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(1, 3, 64, 64))
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 64, 64, device=cuda_device))
+
+
+def test_weights_reload_after_load_state_dict(cuda_device):
+    ref, m = make_pair("resnet34", cuda_device, seed=0)
+    x = O.image_like_input(1, 64, seed=2).to(cuda_device)
+    y0 = m(x).clone()
+    ref2 = O.build("resnet34", seed=5, random_bn=True)
+    m.load_state_dict(ref2.state_dict())
+    y1 = m(x).clone()
+    assert not torch.equal(y0, y1)
+    with torch.no_grad():
+        assert_close_to_oracle(y1.cpu(), ref2(x.cpu()))
+
+
+def test_custom_decoder_channels_via_config(cuda_device):
+    cfg = get_cfg_defaults()
+    cfg.MODEL.NAME = "Unet"
+    cfg.MODEL.ENCODER_WEIGHTS = None
+    cfg.MODEL.DECODER_CHANNELS = [128, 64, 64, 32, 32]
+    m = create_model_from_config(cfg)
+    ref = O.build("resnet34", decoder_channels=(128, 64, 64, 32, 32), seed=1, random_bn=True)
+    m.load_state_dict(ref.state_dict())
+    m = m.to(cuda_device).eval()
+    x = O.image_like_input(1, 64, seed=2)
+    with torch.no_grad():
+        assert_close_to_oracle(m(x.to(cuda_device)).cpu(), ref(x))
+
+
+def test_full_size_properties_config2(cuda_device):
+    """BASELINE config 2 (r34, B=16, 512x512): size-independent properties instead of a full CPU oracle pass:
+    determinism, batch-permutation equivariance (bit-exact: images are independent), mask/logit consistency,
+    and one image checked against the fp32 oracle."""
+    ref, m = make_pair("resnet34", cuda_device)
+    u8 = O.image_like_u8(16, 512, seed=7).to(cuda_device)
+    mask, logits = m.predict_mask(u8, 0.5, return_logits=True)
+    mask, logits = mask.clone(), logits.clone()
+    mask2, logits2 = m.predict_mask(u8, 0.5, return_logits=True)
+    assert torch.equal(mask, mask2) and torch.equal(logits, logits2)
+    assert torch.equal(mask, (logits[:, 0] > 0).to(torch.uint8) * 255)
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(0)).to(cuda_device)
+    mp_, lp = m.predict_mask(u8[perm].contiguous(), 0.5, return_logits=True)
+    assert torch.equal(lp, logits[perm]) and torch.equal(mp_, mask[perm])
+    # batch-size independence: image 3 alone gives the same bits
+    assert torch.equal(m.predict_mask(u8[3:4].contiguous(), 0.5, return_logits=True)[1], logits[3:4])
+    mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+    x0 = (u8[:1].cpu().permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    with torch.no_grad():
+        assert_close_to_oracle(logits[:1].cpu(), ref(x0))

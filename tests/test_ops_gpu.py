@@ -1,0 +1,122 @@
+"""Per-operator parity on the GPU, through the C ABI, against a plain PyTorch fp32 reference of the same
+op on the same bf16-rounded inputs.  Tolerance: |err| <= 1e-2 * max(1, |ref|) (one bf16 rounding of the
+fp32 result, 2^-8 relative, plus fp32 summation-order noise)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.op_cases import CONV_CASES
+from unet_watermark_b200 import _lib, ops, packing
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_matches_fp32_reference(case, cuda_device):
+    name, n, h, w, cin, cout, k, stride, pad, relu, use_res, in_extra, out_extra = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    xbuf = torch.randn(n, h, w, cin + in_extra, generator=g).to(dev).to(torch.bfloat16)
+    x = xbuf[..., in_extra:] if in_extra else xbuf
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = torch.randn(n, ho, wo, cout, generator=g).to(dev).to(torch.bfloat16) if use_res else None
+    wp = packing.pack_taps(wt)
+    obuf = torch.full((n, ho, wo, cout + out_extra), 7.0, dtype=torch.bfloat16, device=dev)
+    out = obuf[..., out_extra:] if out_extra else obuf
+    before = _lib.load().uwm_kernel_launch_count()
+    ops.conv2d(x, wp, bias, k, k, stride, pad, relu=relu, residual=res, out=out)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().view(cout, k, k, cin).permute(0, 3, 1, 2), bias,
+                   stride=stride, padding=pad)
+    if res is not None:
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+    if out_extra:
+        assert bool((obuf[..., :out_extra] == 7.0).all()), "conv wrote outside its channel slice"
+
+
+def test_conv_rejects_bad_arguments(cuda_device):
+    x = torch.zeros(1, 8, 8, 24, dtype=torch.bfloat16, device=cuda_device)      # cin not a multiple of 16
+    w = torch.zeros(16, 9 * 24, dtype=torch.bfloat16, device=cuda_device)
+    b = torch.zeros(16, device=cuda_device)
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.conv2d(x, w, b, 3, 3, 1, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.conv2d(x.cpu(), w.cpu(), b.cpu(), 3, 3, 1, 1)
+
+
+def test_maxpool_exact(cuda_device):
+    g = torch.Generator().manual_seed(1)
+    for shape in ((2, 32, 48, 64), (1, 6, 10, 8), (3, 2, 2, 128)):
+        x = torch.randn(*shape, generator=g).to(cuda_device).to(torch.bfloat16)
+        ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+        assert torch.equal(ops.maxpool3x3s2(x).float(), ref)
+    # pitched input (the stem feature lives inside a concat buffer)
+    buf = torch.randn(2, 16, 16, 96, generator=g).to(cuda_device).to(torch.bfloat16)
+    ref = F.max_pool2d(buf[..., 32:].float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(ops.maxpool3x3s2(buf[..., 32:]).float(), ref)
+
+
+def test_upsample_into_concat_slice_exact(cuda_device):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 12, 20, 64, generator=g).to(cuda_device).to(torch.bfloat16)
+    cat = torch.zeros(2, 24, 40, 96, dtype=torch.bfloat16, device=cuda_device)
+    ops.upsample2x(x, out=cat[..., :64])
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(cat[..., :64].float(), ref)
+    assert bool((cat[..., 64:] == 0).all())
+
+
+def test_prep_input_f32_and_u8(cuda_device):
+    g = torch.Generator().manual_seed(3)
+    xin = torch.randn(2, 3, 64, 96, generator=g).to(cuda_device)
+    xs = ops.prep_input(xin)
+    ref = torch.zeros(2, 32, 48, 16, device=cuda_device)
+    for ph in range(2):
+        for pw in range(2):
+            ref[..., (ph * 2 + pw) * 3:(ph * 2 + pw) * 3 + 3] = xin[:, :, ph::2, pw::2].permute(0, 2, 3, 1)
+    assert torch.equal(xs.float(), ref.to(torch.bfloat16).float())
+    u8 = torch.randint(0, 256, (2, 64, 96, 3), generator=g, dtype=torch.uint8).to(cuda_device)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=cuda_device)
+    std = torch.tensor([0.229, 0.224, 0.225], device=cuda_device)
+    xn = ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    # fused Normalize: equal to the fp32 normalisation up to one bf16 ulp (2^-8 relative)
+    d = (ops.prep_input(u8).float() - ops.prep_input(xn).float()).abs()
+    assert bool((d <= 2 ** -7 * xn.abs().max()).all())
+
+
+def test_stem_as_s2d_conv(cuda_device):
+    g = torch.Generator().manual_seed(4)
+    xin = torch.randn(2, 3, 64, 96, generator=g).to(cuda_device)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5).to(cuda_device)
+    b = torch.randn(64, generator=g).to(cuda_device)
+    y = ops.conv2d(ops.prep_input(xin), packing.pack_stem_s2d(wt), b, 4, 4, 1, 2, relu=True)[:, :32, :48]
+    ref = F.conv2d(xin.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), b, stride=2, padding=3).relu()
+    ref = ref.permute(0, 2, 3, 1)
+    assert bool(((y.float() - ref).abs() <= 1e-2 * ref.abs().clamp_min(1.0)).all())
+
+
+@pytest.mark.parametrize("sigmoid_out", [False, True])
+def test_head_logits_mask_and_threshold_conventions(cuda_device, sigmoid_out):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 96, 16, generator=g).to(cuda_device).to(torch.bfloat16)
+    wh = (torch.randn(1, 16, 3, 3, generator=g) / 12.0).to(cuda_device)
+    bh = torch.tensor([0.1], device=cuda_device)
+    wp = packing.pack_taps(wh)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float()[:1].view(1, 3, 3, 16).permute(0, 3, 1, 2), bh, padding=1)[:, 0]
+    for thr, on_logits in ((0.5, False), (0.5, True), (0.3, False)):
+        out, mask = ops.head(x, wp, packing.pad_bias(bh, 16), threshold=thr, thr_on_logits=on_logits,
+                             apply_sigmoid=sigmoid_out)
+        want = torch.sigmoid(ref) if sigmoid_out else ref
+        assert (out - want).abs().max() < 1e-3
+        cut = thr if on_logits else ops.logit(thr)
+        mref = (ref > cut).to(torch.uint8) * 255
+        wrong = (mask != mref) & ((ref - cut).abs() > 1e-3)       # only ties within fp32 noise may differ
+        assert int(wrong.sum()) == 0
+        assert set(mask.unique().tolist()) <= {0, 255}

@@ -255,7 +255,8 @@ class Unet(nn.Module):
         return d
 
     # ------------------------------------------------------------------ forward
-    def _run(self, x: torch.Tensor, want_logits: bool, threshold, sigmoid_threshold: bool):
+    def _run(self, x: torch.Tensor, want_logits: bool, threshold, sigmoid_threshold: bool,
+             force_sigmoid: bool = False):
         if not x.is_cuda:
             raise RuntimeError("unet_watermark_b200.Unet runs only on CUDA (sm_100a) tensors; there is no CPU "
                                "fallback. Move the model and the input to a B200 (`.to('cuda')`).")
@@ -276,7 +277,8 @@ class Unet(nn.Module):
         with torch.cuda.device(x.device):
             return eng.forward(x, want_logits=want_logits, threshold=threshold,
                                sigmoid_threshold=sigmoid_threshold,
-                               apply_sigmoid=(self.activation_name == "sigmoid"), use_graph=self.use_cuda_graph)
+                               apply_sigmoid=(self.activation_name == "sigmoid" or force_sigmoid),
+                               use_graph=self.use_cuda_graph)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -304,6 +306,13 @@ class Unet(nn.Module):
             sigmoid = True
         logits, mask = self._run(x, return_logits, threshold, sigmoid)
         return (mask, logits) if return_logits else mask
+
+    @torch.no_grad()
+    def predict_proba(self, x: torch.Tensor) -> torch.Tensor:
+        """fp32 ``[B,1,H,W]`` sigmoid(logits), the sigmoid fused into the head kernel
+        (reference src/scripts/watermark_filter.py:136)."""
+        probs, _ = self._run(x, True, None, True, force_sigmoid=True)
+        return probs
 
     def engine(self, b: int, h: int, w: int, device=None) -> Engine:
         dev = torch.device(device) if device is not None else next(self.parameters()).device
