@@ -145,6 +145,14 @@ int    uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int batch,
                          char* names, float* ms, double* flops, double* bytes, int n_max,
                          void* stream);
 
+/* Sizing micro-benchmark (tools/gpu_microbench.py), not on the product path: each of `blocks` CTAs issues
+ * `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16) and writes its clock64() delta to d_cycles. */
+int    uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int blocks, long long* d_cycles,
+                          void* stream);
+
+/* Sizing micro-benchmark: mbarrier ping-pong between two warps, cycles for `iters` round trips. */
+int    uwm_debug_handshake(int iters, int variant, int blocks, long long* d_cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

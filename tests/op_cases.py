@@ -31,6 +31,12 @@ CONV_CASES = [
     ("ragged_48x24",        1, 48, 24,   64,  96, 3, 1, 1, False, False, 0, 0),
     ("tiny_1x1_spatial",    5,  1,  1,  512, 512, 3, 1, 1, True,  True,  0, 0),
     ("tiny_2x2_s2",         3,  2,  2,  256, 512, 3, 2, 1, True,  False, 0, 0),
+    # many tiles per persistent CTA (+ resident-weight mode for n_tiles == 1 and small K*N)
+    ("persist_16_16",       2, 256, 256,  16,  16, 3, 1, 1, True,  False, 0, 0),
+    ("persist_32_16",       1, 256, 384,  32,  16, 3, 1, 1, True,  False, 0, 0),
+    ("persist_64_64_res",   4, 128, 128,  64,  64, 3, 1, 1, True,  True,  0, 0),
+    ("persist_128_128",     4,  96,  96, 128, 128, 3, 1, 1, True,  True,  0, 0),
+    ("persist_64_256_s2",   4, 128, 128,  64, 256, 3, 2, 1, True,  False, 0, 0),
     # resnet50 bottleneck 1x1s and the big decoder K
     ("r50_1x1_64_256",      1, 32, 32,   64, 256, 1, 1, 0, False, False, 0, 0),
     ("r50_1x1_256_64",      1, 32, 32,  256,  64, 1, 1, 0, True,  False, 0, 0),

@@ -23,6 +23,7 @@
 #include "../../include/uwm.h"
 #include "conv_tc.cuh"
 #include "glue.cuh"
+#include "microbench.cuh"
 
 using namespace uwm;
 
@@ -171,20 +172,44 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   a.chunks = s.cin / a.kc;
   a.ntaps = s.ntaps;
   for (int t = 0; t < s.ntaps; ++t) { a.tap_dh[t] = s.dh[t]; a.tap_dw[t] = s.dw[t]; }
-  int bn = std::min(s.cout_pad, 128);
-  while (s.cout_pad % bn) bn -= 16;
+  const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
+  int bn;
+  if (s.cout_pad % 256 == 0 && (long long)m_tiles * (s.cout_pad / 256) * 100 >= 85LL * num_sms()) {
+    bn = 256;                         // N=256 halves the A re-reads and doubles the MMA work per k-step
+  } else {
+    bn = std::min(s.cout_pad, 128);
+    while (s.cout_pad % bn) bn -= 16;
+  }
   a.block_n = bn;
   a.n_tiles = s.cout_pad / bn;
   a.cout = s.cout;
   a.a_stage_bytes = 128u * a.kc * 2u;
   a.b_stage_bytes = ((uint32_t)bn * a.kc * 2u + 1023u) & ~1023u;
-  const uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
-  int stages = (int)((96u * 1024u) / stage_bytes);
-  stages = std::max(2, std::min(stages, 12));
-  stages = std::min(stages, std::max(2, s.ntaps * a.chunks));
+  const int nk = s.ntaps * a.chunks;
+  a.total_tiles = m_tiles * a.n_tiles;
+  const unsigned grid = (unsigned)std::min(a.total_tiles, num_sms());
+  // small layers: keep the whole weight matrix resident in smem (loaded once per persistent CTA)
+  const size_t resident_bytes = (size_t)nk * a.b_stage_bytes;
+  a.b_resident = (a.n_tiles == 1 && resident_bytes <= 80u * 1024u && a.total_tiles >= 2 * (int)grid) ? 1 : 0;
+  const size_t kSmemBudget = 208u * 1024u;
+  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (a.b_resident ? resident_bytes : 0);
+  const uint32_t kstep_bytes = a.a_stage_bytes + (a.b_resident ? 0u : a.b_stage_bytes);
+  // k-steps per ring stage: enough MMA work (>= ~768 cycles at the measured 41-cycle small-N floor) to
+  // amortise one barrier round trip, while keeping at least 3 stages in flight
+  const int mma_cycles = (a.kc / 16) * std::max(41, bn / 2);
+  const int kp_target = (768 + mma_cycles - 1) / mma_cycles;
+  const int kp_max = std::max(1, (int)((kSmemBudget - fixed) / 3 / kstep_bytes));
+  int kp = std::max(1, std::min(std::min(kp_target, kp_max), nk));
+  { const char* e = getenv("UWM_KPACK"); if (e && atoi(e) > 0) kp = std::min(atoi(e), std::min(kp_max, nk)); }
+  const int groups = (nk + kp - 1) / kp;
+  kp = (nk + groups - 1) / groups;
+  a.kpack = kp;
+  const uint32_t ring_stage = (uint32_t)kp * kstep_bytes;
+  int stages = (int)((kSmemBudget - fixed) / ring_stage);
+  stages = std::max(2, std::min(stages, kMaxStages));
   a.stages = stages;
   uint32_t cols = 32;
-  while (cols < (uint32_t)bn) cols <<= 1;
+  while (cols < 2u * (uint32_t)bn) cols <<= 1;     // two accumulators (double buffering)
   a.tmem_cols = cols;
   a.layout_type = (a.kc == 64) ? kLayoutSw128 : (a.kc == 32) ? kLayoutSw64 : kLayoutSw32;
   a.bias = s.bias;
@@ -195,8 +220,9 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   a.head = s.head; a.apply_sigmoid = s.apply_sigmoid;
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
 
-  L->grid = (unsigned)(a.tiles_w * a.tiles_h * a.tiles_n * a.n_tiles);
-  L->smem = 1024 /*align slack*/ + (size_t)stages * stage_bytes + 1024 /*bias*/ + 512 /*barriers*/;
+  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  L->grid = grid;
+  L->smem = fixed + (size_t)stages * ring_stage;
 
   const CUtensorMapSwizzle sw = (a.kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
                               : (a.kc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -231,13 +257,24 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   return UWM_OK;
 }
 
+static int set_conv_attrs() {
+  static bool done = false;
+  if (done) return UWM_OK;
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  done = true;
+  return UWM_OK;
+}
+
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  int rc = set_conv_attrs();
+  if (rc) return rc;
+  switch (L.args.kc) {
+    case 64: conv_tc_kernel<64><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
+    case 32: conv_tc_kernel<32><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
+    default: conv_tc_kernel<16><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
   }
-  conv_tc_kernel<<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args);
   return post_launch("conv_tc_kernel", st);
 }
 
@@ -749,7 +786,8 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
   }
   if (!pl.body) {
     // capture everything between prep and head (all pointers library-owned) once per batch size
-    CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    rc = set_conv_attrs();
+    if (rc) return rc;
     cudaGraph_t g = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed));
     for (size_t i = 1; i + 1 < n; ++i) {
@@ -824,4 +862,21 @@ extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// micro-benchmarks (sizing experiments; not part of the product path)
+// ------------------------------------------------------------------------------------------
+extern "C" int uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int blocks, long long* d_cycles, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = 1024 + (size_t)distinct_stages * (16384 + 32768);
+  CUDA_TRY(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  mma_rate_kernel<<<blocks, 128, smem, st>>>(n, iters, distinct_stages, mode, d_cycles);
+  return post_launch("mma_rate_kernel", st);
+}
+
+extern "C" int uwm_debug_handshake(int iters, int variant, int blocks, long long* d_cycles, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  handshake_kernel<<<blocks, 64, 0, st>>>(iters, variant, d_cycles);
+  return post_launch("handshake_kernel", st);
 }
