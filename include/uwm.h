@@ -70,6 +70,20 @@ int uwm_conv2d_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pi
                          const void* d_res, int res_pitch, int relu,
                          void* d_y, int y_pitch, void* stream);
 
+/* smp DecoderBlock.forward's `F.interpolate(x, scale_factor=2, mode="nearest")`, `torch.cat([x, skip], 1)`
+ * and conv1 (Conv2d + folded BN + ReLU) as ONE kernel: the loader of the
+ * halo-resident conv reads pixel (i>>1, j>>1) of x and pixel (i, j) of skip, so neither the upsampled
+ * tensor nor the concat is written to memory.
+ *   x    : [n,h,w,c_x] bf16 (pitch x_pitch); upsample != 0 -> the conv runs at (2h, 2w)
+ *   skip : [n,H,W,c_skip] bf16 at the conv's resolution, or NULL; weights' K order is [x channels | skip channels]
+ *   wgt  : [cout][kh*kw*(c_x+c_skip)] bf16 (UWM_PACK_TAPS); 'same' padding (2*pad == k-1), stride 1
+ *   y    : [n,H,W,cout] bf16.  c_x, c_skip, cout multiples of 16. */
+int uwm_conv2d_upcat_nhwc_bf16(const void* d_x, int n, int h, int w, int c_x, int x_pitch, int upsample,
+                               const void* d_skip, int c_skip, int skip_pitch,
+                               const void* d_wgt, const float* d_bias, int cout,
+                               int kh, int kw, int pad, int relu,
+                               void* d_y, int y_pitch, void* stream);
+
 /* Segmentation head: conv3x3(cin -> 1, bias) + optional sigmoid + threshold + uint8 mask.
  * Replaces smp SegmentationHead and `(mask > thr)*255`
  * (reference src/predict.py:624-625).  d_logits (fp32 [n,h,w]) and d_mask (uint8 [n,h,w],

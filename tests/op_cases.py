@@ -44,3 +44,19 @@ CONV_CASES = [
     ("r50_1x1_512_2048res", 1,  4,  4,  512, 2048, 1, 1, 0, True,  True,  0, 0),
     ("r50_d0_3x3_3072_256", 1,  8,  8, 3072, 256, 3, 1, 1, True,  False, 0, 0),
 ]
+
+# Fused nearest-2x upsample + concat + conv3x3 (smp DecoderBlock: interpolate, cat, conv1) — uwm_conv2d_upcat_nhwc_bf16.
+# (name, n, h_lo, w_lo, c_x, c_skip, cout, upsample, relu, x_pitch_extra, skip_pitch_extra)
+UPCAT_CASES = [
+    ("d0_up512_skip256_256", 2,  4,  4, 512, 256, 256, True,  True,  0, 0),
+    ("d1_up256_skip128_128", 1,  8,  8, 256, 128, 128, True,  True,  0, 0),
+    ("d2_up128_skip64_64",   1, 16, 16, 128,  64,  64, True,  True,  0, 0),
+    ("d3_up64_skip64_32",    1, 32, 32,  64,  64,  32, True,  True,  0, 0),
+    ("d4_up32_noskip_16",    1, 32, 64,  32,   0,  16, True,  True,  0, 0),
+    ("r50_d0_up2048_skip1024", 1, 4, 4, 2048, 1024, 256, True, True, 0, 0),
+    ("upcat_ragged_h",       2, 12, 20,  32,  16,  48, True,  False, 0, 0),    # 24x40: H not a multiple of 16, kc=16
+    ("upcat_ragged_w",       3,  5,  7,  64,  32,  32, True,  True,  0, 0),    # 10x14: W not a multiple of 8
+    ("cat_noup",             1, 16, 24,  64,  64,  64, False, True,  0, 0),
+    ("upcat_pitched",        2,  8,  8,  64,  64,  64, True,  True,  32, 64),
+    ("upcat_persistent",     2, 128, 128, 32,  0,  16, True,  True,  0, 0),    # many tiles per CTA
+]

@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.op_cases import CONV_CASES
+from tests.op_cases import CONV_CASES, UPCAT_CASES
 from unet_watermark_b200 import _lib, ops, packing
 
 pytestmark = pytest.mark.gpu
@@ -39,6 +39,39 @@ def test_conv_matches_fp32_reference(case, cuda_device):
     assert bool((err <= 1e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
     if out_extra:
         assert bool((obuf[..., :out_extra] == 7.0).all()), "conv wrote outside its channel slice"
+
+
+@pytest.mark.parametrize("case", UPCAT_CASES, ids=[c[0] for c in UPCAT_CASES])
+def test_upcat_conv_matches_fp32_reference(case, cuda_device):
+    """interpolate(nearest, x2) + cat + conv3x3 + bias + ReLU in one kernel vs the same three torch ops."""
+    name, n, h, w, cx, cs, cout, up, relu, x_extra, s_extra = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    xbuf = torch.randn(n, h, w, cx + x_extra, generator=g).to(dev).to(torch.bfloat16)
+    x = xbuf[..., x_extra:] if x_extra else xbuf
+    ho, wo = (2 * h, 2 * w) if up else (h, w)
+    skip = None
+    if cs:
+        sbuf = torch.randn(n, ho, wo, cs + s_extra, generator=g).to(dev).to(torch.bfloat16)
+        skip = sbuf[..., :cs] if s_extra else sbuf
+    cin = cx + cs
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    wp = packing.pack_taps(wt)
+    before = _lib.load().uwm_kernel_launch_count()
+    out = ops.conv2d_upcat(x, skip, wp, bias, relu=relu, upsample=up)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    xi = x.float().permute(0, 3, 1, 2)
+    if up:
+        xi = F.interpolate(xi, scale_factor=2, mode="nearest")
+    if skip is not None:
+        xi = torch.cat([xi, skip.float().permute(0, 3, 1, 2)], dim=1)
+    ref = F.conv2d(xi, wp.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), bias, padding=1)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
 
 
 def test_conv_rejects_bad_arguments(cuda_device):

@@ -1,35 +1,72 @@
-"""Time single conv layers (all distinct r34@512^2 B=16 shapes) through the C ABI.  UWM_DBG=1|2 isolates TMA / MMA."""
-import os, sys
-import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from unet_watermark_b200 import ops, packing
+"""Time single conv layers (all distinct r34@512^2 B=16 stride-1 shapes) through the C ABI.
 
-SHAPES = [  # name, n, h, w, cin, cout, k, stride
-    ("layer1 64->64 @128", 16, 128, 128, 64, 64, 3, 1),
-    ("layer2 128->128 @64", 16, 64, 64, 128, 128, 3, 1),
-    ("layer3 256->256 @32", 16, 32, 32, 256, 256, 3, 1),
-    ("layer4 512->512 @16", 16, 16, 16, 512, 512, 3, 1),
-    ("dec0 768->256 @32", 16, 32, 32, 768, 256, 3, 1),
-    ("dec2 192->64 @128", 16, 128, 128, 192, 64, 3, 1),
-    ("dec3 128->32 @256", 16, 256, 256, 128, 32, 3, 1),
-    ("dec4 32->16 @512", 16, 512, 512, 32, 16, 3, 1),
-    ("dec4 16->16 @512", 16, 512, 512, 16, 16, 3, 1),
+    python tools/gpu_conv_bench.py [--dbg 0,1,2,4,7] [--filter dec4]
+
+UWM_DBG bit mask (bench-only; results are garbage when set): 1 skip activation loads, 2 skip MMAs,
+4 skip epilogue.  Comparing the columns shows which of loader / tensor pipe / epilogue bounds a layer.
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unet_watermark_b200 import ops, packing  # noqa: E402
+
+SHAPES = [  # name, n, h, w, cin (x), cskip, cout, upsample
+    ("layer1 64->64 @128", 16, 128, 128, 64, 0, 64, False),
+    ("layer2 128->128 @64", 16, 64, 64, 128, 0, 128, False),
+    ("layer3 256->256 @32", 16, 32, 32, 256, 0, 256, False),
+    ("layer4 512->512 @16", 16, 16, 16, 512, 0, 512, False),
+    ("dec0 up512+256->256 @32", 16, 16, 16, 512, 256, 256, True),
+    ("dec1 up256+128->128 @64", 16, 32, 32, 256, 128, 128, True),
+    ("dec2 up128+64->64 @128", 16, 64, 64, 128, 64, 64, True),
+    ("dec3 up64+64->32 @256", 16, 128, 128, 64, 64, 32, True),
+    ("dec3 32->32 @256", 16, 256, 256, 32, 0, 32, False),
+    ("dec4 up32->16 @512", 16, 256, 256, 32, 0, 16, True),
+    ("dec4 16->16 @512", 16, 512, 512, 16, 0, 16, False),
 ]
-dev = torch.device("cuda:0")
-for name, n, h, w, cin, cout, k, st in SHAPES:
-    x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
-    wp = packing.pack_taps(torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5)
-    b = torch.zeros(cout, device=dev)
-    out = torch.empty(n, h // st, w // st, cout, dtype=torch.bfloat16, device=dev)
-    for _ in range(3):
-        ops.conv2d(x, wp, b, k, k, st, k // 2, relu=True, out=out)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    for _ in range(10):
-        ops.conv2d(x, wp, b, k, k, st, k // 2, relu=True, out=out)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    fl = 2.0 * n * (h // st) * (w // st) * cin * cout * k * k
-    by = 2.0 * (x.numel() + out.numel())
-    print(f"{name:<24s} {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TF/s  {by/ms/1e6:7.1f} GB/s(algorithmic)", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dbg", default="0")
+    ap.add_argument("--filter", default="")
+    args = ap.parse_args()
+    dbgs = [int(v) for v in args.dbg.split(",")]
+    dev = torch.device("cuda:0")
+    print(f"{'layer':<28s}" + "".join(f"  dbg={d:<2d} us" for d in dbgs) + "   TF/s(dbg0)  GB/s(dbg0, algorithmic)")
+    for name, n, h, w, cx, cs, cout, up in SHAPES:
+        if args.filter not in name:
+            continue
+        x = torch.randn(n, h, w, cx, device=dev).to(torch.bfloat16)
+        ho, wo = (2 * h, 2 * w) if up else (h, w)
+        skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
+        cin = cx + cs
+        wp = packing.pack_taps(torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5)
+        b = torch.zeros(cout, device=dev)
+        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+        times = []
+        for d in dbgs:
+            os.environ["UWM_DBG"] = str(d)
+            for _ in range(3):
+                ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            for _ in range(10):
+                ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 10)
+        os.environ["UWM_DBG"] = "0"
+        fl = 2.0 * n * ho * wo * cin * cout * 9
+        by = 2.0 * (x.numel() + out.numel() + (skip.numel() if skip is not None else 0))
+        ms = times[0]
+        print(f"{name:<28s}" + "".join(f"  {t * 1e3:9.1f}" for t in times) +
+              f"   {fl / ms / 1e9:8.1f}   {by / ms / 1e6:8.1f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

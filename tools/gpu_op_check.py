@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.op_cases import CONV_CASES  # noqa: E402
+from tests.op_cases import CONV_CASES, UPCAT_CASES  # noqa: E402
 from unet_watermark_b200 import ops, packing  # noqa: E402
 
 
@@ -48,6 +48,36 @@ def conv_case(case, dev, seed=0):
     return err.max().item(), ref.abs().max().item(), bad, untouched
 
 
+def upcat_case(case, dev, seed=0):
+    name, n, h, w, cx, cs, cout, up, relu, x_extra, s_extra = case
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xbuf = torch.randn(n, h, w, cx + x_extra, generator=g).to(dev).to(torch.bfloat16)
+    x = xbuf[..., x_extra:] if x_extra else xbuf
+    ho, wo = (2 * h, 2 * w) if up else (h, w)
+    skip = None
+    if cs:
+        sbuf = torch.randn(n, ho, wo, cs + s_extra, generator=g).to(dev).to(torch.bfloat16)
+        skip = sbuf[..., :cs] if s_extra else sbuf
+    cin = cx + cs
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    wp = packing.pack_taps(wt)
+    out = ops.conv2d_upcat(x, skip, wp, bias, relu=relu, upsample=up)
+    torch.cuda.synchronize()
+    xi = x.float().permute(0, 3, 1, 2)
+    if up:
+        xi = F.interpolate(xi, scale_factor=2, mode="nearest")
+    if skip is not None:
+        xi = torch.cat([xi, skip.float().permute(0, 3, 1, 2)], dim=1)
+    ref = F.conv2d(xi, wp.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), bias, padding=1)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    bad = (err > 1e-2 * ref.abs().clamp_min(1.0)).float().mean().item()
+    return err.max().item(), ref.abs().max().item(), bad
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--filter", default="")
@@ -68,6 +98,22 @@ def main():
         except Exception as ex:  # noqa: BLE001
             nfail += 1
             print(f"EXC  conv {case[0]}: {ex}", flush=True)
+            traceback.print_exc()
+            if "CUDA" in str(ex) or "fault" in str(ex):
+                print("aborting after CUDA error")
+                sys.exit(2)
+
+    for case in UPCAT_CASES:
+        if args.filter not in case[0]:
+            continue
+        try:
+            e, m, bad = upcat_case(case, dev)
+            ok = bad == 0.0
+            print(f"{'OK  ' if ok else 'FAIL'} upcat {case[0]:<24s} max_err={e:.4g} ref_max={m:.4g} bad_frac={bad:.4g}", flush=True)
+            nfail += (not ok)
+        except Exception as ex:  # noqa: BLE001
+            nfail += 1
+            print(f"EXC  upcat {case[0]}: {ex}", flush=True)
             traceback.print_exc()
             if "CUDA" in str(ex) or "fault" in str(ex):
                 print("aborting after CUDA error")

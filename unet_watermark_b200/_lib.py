@@ -42,6 +42,9 @@ SIGNATURES = {
     "uwm_conv2d_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P,
                                        C.c_int, _P]),
+    "uwm_conv2d_upcat_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int,
+                                             C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
+                                             C.c_int, _P]),
     "uwm_head_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,
                                      _P, C.c_float, _P]),
     "uwm_maxpool3x3s2_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libuwm_b200.so")
 SOURCES = ["uwm_api.cu"]
-DEPS = ["uwm_api.cu", "conv_tc.cuh", "glue.cuh", "ptx_sm100.cuh", os.path.join("..", "..", "include", "uwm.h")]
+DEPS = ["uwm_api.cu", "conv_tc.cuh", "conv_halo.cuh", "glue.cuh", "ptx_sm100.cuh", "microbench.cuh", os.path.join("..", "..", "include", "uwm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

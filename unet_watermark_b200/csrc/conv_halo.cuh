@@ -1,0 +1,424 @@
+// Halo-resident implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) for stride-1 k x k convs,
+// with the decoder's nearest-2x upsample and skip concat fused into the activation loader.
+//
+//   out[n,h,w,co] = epilogue( sum_{tap,ci} in[n, h+dh(tap), w+dw(tap), ci] * wgt[co, tap, ci] )
+//   in = concat_c( up2x?(src0), src1 )          (src1 optional; up2x = F.interpolate(nearest, x2))
+//
+// Why a second conv kernel: conv_tc.cuh re-fetches the 128-pixel activation tile from L2 once per
+// filter tap (9x for a 3x3), and the L2->SM fabric (~42 B/clk/SM) - not the tensor pipe - bounds every
+// layer.  Here a CTA loads the HALO of its output tile ONCE per 64-channel chunk and every tap reads a
+// shifted window of that one copy.  A tile is TG sub-tiles of 8 (w) x 16 (h) pixels side by side; each
+// sub-tile is one M=128 accumulator, all of them share the halo and every weight slice:
+//
+//   smem A stage = [kc/8 channel groups][halo pixels][8 channels = 16 B]      (no-swizzle K-major)
+//     core matrix  = 8 consecutive pixels x 16 B = 128 contiguous bytes
+//     SBO (8-row group stride, M direction) = halo_width * 16 B   -> next image row of the tile
+//     LBO (core-matrix stride, K direction) = plane_bytes         -> next 8-channel group
+//     tap (r,c), sub-tile g: descriptor start address += (r*halo_width + c + 8*g) * 16 B
+//
+// Loader warps fill a stage with 16-byte cp.async (zero-fill outside the image = conv padding; the
+// source pixel is (h>>1, w>>1) for an upsampled source, so neither the upsampled tensor nor the concat
+// ever exists in HBM) and signal an mbarrier through cp.async.mbarrier.arrive.  Weights take the same
+// route as in conv_tc.cuh: TMA into 128B/64B/32B-swizzled K-major slices, resident in smem for the small
+// layers or streamed through their own ring.
+//
+// Filter shape, TG and the weight mode are template parameters: ncu shows the single MMA-issuing thread is
+// the critical resource of the small layers (9 MMAs of 32 cycles per 128 pixels against ~350 issue-side
+// instructions per tile in a generic loop), so its loop is fully unrolled with immediate descriptor offsets
+// and TG sub-tiles share every wait/commit.
+//
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0    weight TMA producer          warp 1    TMEM owner + tcgen05.mma issuer
+//   warps 2-5 epilogue (TMEM -> bias/residual/ReLU -> bf16 NHWC, or head: logits / uint8 mask)
+//   warps 6-9 activation loaders
+#pragma once
+#include "conv_tc.cuh"
+
+namespace uwm {
+
+constexpr int kHaloThreads = 320;
+constexpr int kHaloLoaderThreads = 128;
+constexpr int kHaloLoaderWarp0 = 6;
+constexpr int kHaloTW = 8, kHaloTH = 16;
+constexpr int kHaloMaxStages = 16;
+
+// geometry shared by host and device
+__host__ __device__ constexpr int halo_pw(int tg, int kw) { return kHaloTW * tg + kw - 1; }
+__host__ __device__ constexpr int halo_npix(int tg, int kh, int kw) { return halo_pw(tg, kw) * (kHaloTH + kh - 1); }
+// plane stride = 4 (mod 8) sixteen-byte units: the 8 channel groups of one pixel land in distinct banks
+__host__ __device__ constexpr uint32_t halo_plane_bytes(int tg, int kh, int kw) {
+  return (((uint32_t)halo_npix(tg, kh, kw) * 16u + 127u) & ~127u) + 64u;
+}
+
+// n / d for n < 2^31 with a precomputed multiplier (host: make_fastdiv)
+struct FastDiv { uint32_t mul, shr, d; };
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+
+struct HaloSrc {
+  const __nv_bfloat16* ptr;   // NHWC, already offset to the first channel this conv reads
+  long long pitch;            // elements between consecutive pixels
+  int h, w;                   // spatial size of the stored tensor (half the conv's size when up == 1)
+  int up;                     // 1: nearest-2x upsample on the fly
+};
+
+struct HaloKArgs {
+  // geometry: stride 1, output size == (virtual) input size
+  int n_img, h, w;
+  int tiles_w, tiles_h, n_tiles, total_tiles;
+  FastDiv div_ntiles, div_tw, div_th;
+  // K loop: chunks of kc channels (one A stage each), all taps per chunk
+  int chunks;
+  int split_chunk;                          // chunks [0,split) come from src[0], the rest from src[1]
+  int dh_min, dw_min;                       // offset of tap (0,0): tap (r,c) reads pixel (h+dh_min+r, w+dw_min+c)
+  uint32_t pw_magic;                        // p / pw == (p * pw_magic) >> 16 for p < npix
+  int a_stages;
+  HaloSrc src[2];
+  // weights
+  int cin_total;                            // K index of (tap, chunk) = tap*cin_total + chunk*kc
+  int block_n, cout;
+  int kpb, b_stages;                        // streamed weights: kpb taps per stage (divides the tap count)
+  uint32_t b_slice_bytes;                   // one (tap, chunk) slice, multiple of 1024
+  uint32_t tmem_cols;
+  // epilogue
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* out;
+  long long res_pitch, out_pitch;
+  int relu;
+  int head, apply_sigmoid;
+  float* logits;
+  uint8_t* mask;
+  float thr_logit;
+  int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
+};
+
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` (without raising its pending count) once all cp.async issued so far by this thread landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Waits with the watchdog kept out of line: the MMA thread's instruction footprint matters (i-cache).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// tcgen05.mma with separate descriptor halves; ACC: accumulate into D unconditionally, else only when acc != 0
+template <bool ACC>
+__device__ __forceinline__ void umma_halo(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t acc) {
+  if (ACC) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+  } else {
+    umma_bf16_lohi2(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+  }
+}
+
+struct HaloTile { int n_tile, w0, h0, img; };
+template <int TG>
+__device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
+  HaloTile t;
+  int mt = fast_div(tile, p.div_ntiles);
+  t.n_tile = tile - mt * p.n_tiles;
+  int q = fast_div(mt, p.div_tw);
+  t.w0 = (mt - q * p.tiles_w) * (kHaloTW * TG);
+  t.img = fast_div(q, p.div_th);
+  t.h0 = (q - t.img * p.tiles_h) * kHaloTH;
+  return t;
+}
+
+template <int KC, int KH, int KW, int TG, bool RESIDENT>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ HaloKArgs p) {
+  constexpr int NT = KH * KW;
+  constexpr int CPS = KC / 8;                               // 8-channel planes per stage
+  constexpr int LOG2_CPS = (KC == 64) ? 3 : (KC == 32) ? 2 : 1;
+  constexpr int PW = halo_pw(TG, KW);
+  constexpr int NPIX = halo_npix(TG, KH, KW);
+  constexpr uint32_t PLANE_BYTES = halo_plane_bytes(TG, KH, KW);
+  constexpr uint32_t PLANE_UNITS = PLANE_BYTES >> 4;
+  constexpr uint32_t A_STAGE_BYTES = CPS * PLANE_BYTES;
+  constexpr int ITEMS = NPIX * CPS;                         // 16-byte pieces per stage
+  constexpr uint32_t B_LAYOUT = (KC == 64) ? kLayoutSw128 : (KC == 32) ? kLayoutSw64 : kLayoutSw32;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // weight slices need 1024-B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int nk = NT * p.chunks;
+  const uint32_t b_stage_bytes = (uint32_t)p.kpb * p.b_slice_bytes;
+  const uint32_t b_bytes_total = RESIDENT ? (uint32_t)nk * p.b_slice_bytes : (uint32_t)p.b_stages * b_stage_bytes;
+  const uint32_t b_base = smem_base;
+  const uint32_t a_base = smem_base + b_bytes_total;
+  const uint32_t misc_off = b_bytes_total + (uint32_t)p.a_stages * A_STAGE_BYTES;
+  const uint32_t bar_base = (smem_base + misc_off + 7u) & ~7u;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (kHaloMaxStages + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxStages + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (3 * kHaloMaxStages + s); };
+  auto accf_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + a); };
+  auto acce_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + 2 + a); };
+  const uint32_t bres_bar = bar_base + 8u * (4 * kHaloMaxStages + 4);
+  uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 6));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 4); }
+    mbar_init(bres_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_wgt);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(s_tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem_slot;
+  const int G = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight TMA producer
+    const uint32_t slice_tx = (uint32_t)p.block_n * KC * 2u;
+    if (RESIDENT) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)nk * slice_tx);
+        for (int ch = 0; ch < p.chunks; ++ch)
+          for (int tap = 0; tap < NT; ++tap)
+            tma_load_2d(b_base + (uint32_t)(ch * NT + tap) * p.b_slice_bytes, &tm_wgt, bres_bar,
+                        tap * p.cin_total + ch * KC, 0);
+      }
+      __syncwarp();
+    } else {
+      const bool leader = elect_one();
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
+        const int ncol = (tile - fast_div(tile, p.div_ntiles) * p.n_tiles) * p.block_n;
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
+            if (leader) {
+              mbar_wait(bempty_bar(s), ph ^ 1u);
+              mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)p.kpb * slice_tx);
+              const uint32_t dst = b_base + (uint32_t)s * b_stage_bytes;
+              for (int j = 0; j < p.kpb; ++j)
+                tma_load_2d(dst + (uint32_t)j * p.b_slice_bytes, &tm_wgt, bfull_bar(s),
+                            (tap0 + j) * p.cin_total + ch * KC, ncol);
+            }
+            if (++s == p.b_stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one elected thread)
+    const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+    // A: no-swizzle K-major.  hi = SBO (halo row) | version;  lo = start>>4 | LBO (plane stride) << 16
+    constexpr uint32_t a_hi = (uint32_t)PW | (1u << 14);
+    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (PLANE_UNITS << 16);
+    constexpr uint32_t a_stage_units = A_STAGE_BYTES >> 4;
+    // B: swizzled K-major slices, rows of KC*2 bytes
+    constexpr uint32_t b_hi = ((8u * KC * 2u) >> 4) | (1u << 14) | (B_LAYOUT << 29);
+    const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_slice_units = p.b_slice_bytes >> 4;
+    const uint32_t b_stage_units = b_stage_bytes >> 4;
+    const uint32_t bn = (uint32_t)p.block_n;
+    const bool skip_mma = p.dbg & 2;
+    if (elect_one()) {
+      if (RESIDENT) mbar_wait(bres_bar, 0);
+      int sa = 0; uint32_t pha = 0;
+      int sb = 0; uint32_t phb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
+        const int acc = it & 1;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)acc * (TG * bn);
+        mbar_wait_fast(acce_bar(acc), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          mbar_wait_fast(afull_bar(sa), pha);
+          fence_proxy_async_smem();        // loaders wrote through the generic proxy (cp.async)
+          tc_fence_after();
+          const uint32_t a_st = a_lo0 + (uint32_t)sa * a_stage_units;
+          uint32_t b_lo = b_lo0 + (uint32_t)(ch * NT) * b_slice_units;   // resident: slice (ch, tap 0)
+          int j = 0;                                                      // streamed: slice inside the stage
+          if (!skip_mma) {
+#pragma unroll
+            for (int tap = 0; tap < NT; ++tap) {
+              const uint32_t shift = (uint32_t)((tap / KW) * PW + (tap % KW));
+              if (!RESIDENT && j == 0) {
+                mbar_wait_fast(bfull_bar(sb), phb);
+                tc_fence_after();
+                b_lo = b_lo0 + (uint32_t)sb * b_stage_units;
+              }
+#pragma unroll
+              for (int g = 0; g < TG; ++g) {
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  if (tap == 0 && k == 0)
+                    umma_halo<false>(tmem_acc + g * bn, a_st + shift + 8u * g + 2u * k * PLANE_UNITS, a_hi,
+                                     b_lo + 2u * k, b_hi, idesc, (uint32_t)ch);
+                  else
+                    umma_halo<true>(tmem_acc + g * bn, a_st + shift + 8u * g + 2u * k * PLANE_UNITS, a_hi,
+                                    b_lo + 2u * k, b_hi, idesc, 1u);
+                }
+              }
+              b_lo += b_slice_units;
+              if (!RESIDENT && ++j == p.kpb) {
+                j = 0;
+                umma_commit(bempty_bar(sb));
+                if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+              }
+            }
+          } else if (!RESIDENT) {
+            for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
+              mbar_wait_fast(bfull_bar(sb), phb);
+              umma_commit(bempty_bar(sb));
+              if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+            }
+          }
+          umma_commit(aempty_bar(sa));
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+        }
+        umma_commit(accf_bar(acc));
+      }
+    }
+  } else if (warp < kHaloLoaderWarp0) {
+    // ------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;           // accumulator row == pixel of the 8x16 sub-tile
+    const int wi = row & (kHaloTW - 1);
+    const int hi = row >> 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
+      const int acc = it & 1;
+      const HaloTile t = halo_decode<TG>(p, tile);
+      const int oh = t.h0 + hi;
+      const int col0 = t.n_tile * p.block_n;
+
+      if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < TG; ++g) {
+        const int ow = t.w0 + g * kHaloTW + wi;
+        const bool valid = (ow < p.w) && (oh < p.h);
+        const long long pix = ((long long)t.img * p.h + oh) * p.w + ow;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * TG + g) * p.block_n);
+
+        if (p.dbg & 4) {
+          // bench-only: no epilogue work
+        } else if (p.head) {
+          uint32_t v[16];
+          tmem_ld_x16(taddr, v);
+          tmem_ld_wait();
+          if (valid) {
+            const float z = __uint_as_float(v[0]) + __ldg(p.bias);
+            if (p.logits) p.logits[pix] = p.apply_sigmoid ? 1.f / (1.f + __expf(-z)) : z;
+            if (p.mask) p.mask[pix] = (z > p.thr_logit) ? 255 : 0;
+          }
+        } else {
+          __nv_bfloat16* orow = p.out + pix * p.out_pitch + col0;
+          const __nv_bfloat16* rrow = p.res ? p.res + pix * p.res_pitch + col0 : nullptr;
+          const float4* brow = reinterpret_cast<const float4*>(p.bias + col0);
+          const int ncols = min(p.block_n, p.cout - col0);
+          for (int c = 0; c < ncols; c += 16) {
+            uint32_t v[16];
+            tmem_ld_x16(taddr + c, v);
+            const float4 b0 = __ldg(brow + (c >> 2)), b1 = __ldg(brow + (c >> 2) + 1);
+            const float4 b2 = __ldg(brow + (c >> 2) + 2), b3 = __ldg(brow + (c >> 2) + 3);
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+            if (rrow && valid) {
+              r0 = *reinterpret_cast<const uint4*>(rrow + c);
+              r1 = *reinterpret_cast<const uint4*>(rrow + c + 8);
+            }
+            tmem_ld_wait();
+            if (valid) {
+              float f[16];
+              const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
+                                    b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
+              if (rrow) {
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(rr[j]); f[2 * j + 1] += bf16_hi(rr[j]); }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+              o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+              o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+              *reinterpret_cast<uint4*>(orow + c) = o0;
+              *reinterpret_cast<uint4*>(orow + c + 8) = o1;
+            }
+          }
+        }
+      }  // sub-tiles
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(acc));
+    }
+  } else {
+    // ------------------------------------------------------------ activation loaders (4 warps)
+    const int lt = threadIdx.x - kHaloLoaderWarp0 * 32;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
+      const HaloTile t = halo_decode<TG>(p, tile);
+      const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        const HaloSrc& S = p.src[ch < p.split_chunk ? 0 : 1];
+        const int cbase = (ch < p.split_chunk ? ch : ch - p.split_chunk) * KC;
+        const __nv_bfloat16* img = S.ptr + (long long)t.img * S.h * S.w * S.pitch + cbase;
+        const int up = S.up, sw_ = S.w;
+        const int pitch = (int)S.pitch;
+        if (lane == 0) mbar_wait(aempty_bar(s), ph ^ 1u);
+        __syncwarp();
+        const uint32_t dst0 = a_base + (uint32_t)s * A_STAGE_BYTES;
+        if (!(p.dbg & 1)) {
+#pragma unroll 4
+          for (int i = lt; i < ITEMS; i += kHaloLoaderThreads) {
+            const int c = i & (CPS - 1);
+            const int px = i >> LOG2_CPS;
+            const int hh = (int)(((uint32_t)px * p.pw_magic) >> 16);
+            const int ww = px - hh * PW;
+            const int ih = hbase + hh, iw = wbase + ww;
+            const bool valid = ((unsigned)ih < (unsigned)p.h) && ((unsigned)iw < (unsigned)p.w);
+            const int off = valid ? ((ih >> up) * sw_ + (iw >> up)) * pitch + c * 8 : 0;   // < 2^31: checked on the host
+            cp_async_16_zfill(dst0 + (uint32_t)c * PLANE_BYTES + (uint32_t)px * 16u, img + off, valid ? 16u : 0u);
+          }
+        }
+        cp_async_mbar_arrive_noinc(afull_bar(s));
+        if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace uwm

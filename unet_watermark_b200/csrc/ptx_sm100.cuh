@@ -159,6 +159,21 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with independent hi halves for A and B (different layouts: no-swizzle halo A, swizzled B).
+__device__ __forceinline__ void umma_bf16_lohi2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

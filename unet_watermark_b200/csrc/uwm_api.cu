@@ -22,6 +22,7 @@
 
 #include "../../include/uwm.h"
 #include "conv_tc.cuh"
+#include "conv_halo.cuh"
 #include "glue.cuh"
 #include "microbench.cuh"
 
@@ -102,8 +103,12 @@ static int num_sms() {
 // ------------------------------------------------------------------------------------------
 struct ConvSpec {
   const void* x = nullptr;        // activation base (already offset to the channel slice)
-  int n = 0, h = 0, w = 0, cin = 0;
+  int n = 0, h = 0, w = 0, cin = 0; // h, w: conv input size (the UPSAMPLED size when up1)
   long long x_pitch = 0;
+  int up1 = 0;                    // x is stored at (h/2, w/2): nearest-2x upsample fused into the loader
+  const void* x2 = nullptr;       // optional second source, concatenated after x along channels
+  int cin2 = 0;
+  long long x2_pitch = 0;
   const void* wgt = nullptr;      // [cout_pad][ntaps*cin]
   const float* bias = nullptr;
   int cout = 0, cout_pad = 0;
@@ -123,8 +128,11 @@ struct ConvSpec {
 };
 
 struct ConvLaunch {
+  int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
+  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0;   // halo: template instantiation
   CUtensorMap tm_act, tm_wgt;
   ConvKArgs args;
+  HaloKArgs hargs;
   unsigned grid = 0;
   size_t smem = 0;
 };
@@ -146,7 +154,208 @@ static void choose_tile(int W, int H, int N, int stride, int* tw, int* th, int* 
   }
 }
 
+
+static FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = (uint32_t)d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    int l = 0; while ((1LL << l) < d) ++l;          // ceil(log2 d)
+    const int p = 31 + l;
+    f.mul = (uint32_t)(((1ULL << p) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UWM_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+// Halo-resident kernel (conv_halo.cuh): stride-1 convs, optional fused upsample + concat.
+static int build_halo(const ConvSpec& s, ConvLaunch* L) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if (s.stride != 1) return fail(UWM_EINVAL, "halo conv: stride %d unsupported", s.stride);
+  if (s.cin % 16 || s.cin2 % 16) return fail(UWM_EINVAL, "halo conv: cin=%d+%d must be multiples of 16", s.cin, s.cin2);
+  if (s.cout_pad % 16) return fail(UWM_EINVAL, "halo conv: cout_pad=%d must be a multiple of 16", s.cout_pad);
+  if (s.ntaps < 1 || s.ntaps > kMaxTaps) return fail(UWM_EINVAL, "halo conv: %d taps unsupported", s.ntaps);
+  if (s.h_out != s.h || s.w_out != s.w) return fail(UWM_EINVAL, "halo conv: needs 'same' padding (%dx%d -> %dx%d)", s.h, s.w, s.h_out, s.w_out);
+  if (s.up1 && ((s.h | s.w) & 1)) return fail(UWM_EINVAL, "halo conv: upsampled size %dx%d must be even", s.h, s.w);
+  if ((s.x_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.x) & 15) ||
+      (s.x2 && ((s.x2_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.x2) & 15))))
+    return fail(UWM_EINVAL, "halo conv: activation base/pitch must be 16-byte aligned");
+  if (!s.head && ((s.out_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.out) & 15)))
+    return fail(UWM_EINVAL, "halo conv: output base/pitch must be 16-byte aligned");
+  if (s.res && ((s.res_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.res) & 15)))
+    return fail(UWM_EINVAL, "halo conv: residual base/pitch must be 16-byte aligned");
+
+  L->halo = 1;
+  HaloKArgs& a = L->hargs;
+  memset(&a, 0, sizeof(a));
+  a.n_img = s.n; a.h = s.h; a.w = s.w;
+  const int cin_total = s.cin + (s.x2 ? s.cin2 : 0);
+  int kc = 64;
+  while (kc > 16 && (s.cin % kc || (s.x2 && s.cin2 % kc))) kc >>= 1;
+  a.chunks = cin_total / kc;
+  a.split_chunk = s.cin / kc;
+  const int cps = kc / 8;
+  // taps must be the full kh x kw rectangle in row-major order (taps_rect / the stem's 4x4)
+  int dh_min = 127, dh_max = -128, dw_min = 127, dw_max = -128;
+  for (int t = 0; t < s.ntaps; ++t) {
+    dh_min = std::min(dh_min, (int)s.dh[t]); dh_max = std::max(dh_max, (int)s.dh[t]);
+    dw_min = std::min(dw_min, (int)s.dw[t]); dw_max = std::max(dw_max, (int)s.dw[t]);
+  }
+  const int kh = dh_max - dh_min + 1, kw = dw_max - dw_min + 1;
+  if (kh * kw != s.ntaps) return fail(UWM_EINVAL, "halo conv: taps are not a full %dx%d rectangle", kh, kw);
+  for (int t = 0; t < s.ntaps; ++t)
+    if (s.dh[t] != dh_min + t / kw || s.dw[t] != dw_min + t % kw)
+      return fail(UWM_EINVAL, "halo conv: taps must be in row-major order");
+  if (!((kh == 3 && kw == 3) || (kh == 4 && kw == 4 && kc == 16)))
+    return fail(UWM_EINVAL, "halo conv: %dx%d filters with %d-channel chunks are not instantiated", kh, kw, kc);
+  a.dh_min = dh_min; a.dw_min = dw_min;
+  a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x);
+  a.src[0].pitch = s.x_pitch; a.src[0].up = s.up1 ? 1 : 0;
+  a.src[0].h = s.up1 ? s.h / 2 : s.h; a.src[0].w = s.up1 ? s.w / 2 : s.w;
+  a.src[1].ptr = static_cast<const __nv_bfloat16*>(s.x2 ? s.x2 : s.x);
+  a.src[1].pitch = s.x2 ? s.x2_pitch : s.x_pitch; a.src[1].up = 0; a.src[1].h = s.h; a.src[1].w = s.w;
+  for (int i = 0; i < 2; ++i)
+    if ((long long)a.src[i].h * a.src[i].w * a.src[i].pitch >= (1LL << 31))
+      return fail(UWM_EINVAL, "halo conv: one image of a source exceeds 2^31 elements");
+  a.cin_total = cin_total;
+  const int nk = s.ntaps * a.chunks;
+
+  // ---- tile selection: N tile (bn) x sub-tiles per tile (tg), by a small cost model (cycles) ----------
+  //   issue  : the one MMA-issuing thread: ~60 instr per stage + ~12 per tap + ~3 per MMA, ~6 clk each (ncu)
+  //   tensor : tg * nk * (kc/16) MMAs of max(32, bn/2) clk   (M=128: 32-clk floor below N=64)
+  //   L2     : halo(tg)*cin*2 + (weights streamed ? bn*K*2 : 0) bytes per tile; ~64 B/clk per SM, 6300 B/clk chip
+  const size_t kBudget = 206u * 1024u;            // rings + resident weights (barriers/alignment slack on top)
+  const int sms = num_sms();
+  struct Cand { int bn, tg; bool resident; double cost; } best = {0, 0, false, 1e30};
+  std::vector<int> bns;
+  if (s.cout_pad <= 64) bns.push_back(s.cout_pad);
+  else for (int c : {256, 128, 64}) if (s.cout_pad % c == 0) bns.push_back(c);
+  if (bns.empty()) { int b = std::min(s.cout_pad, 256); while (s.cout_pad % b) b -= 16; bns.push_back(b); }
+  const int w8 = (s.w + kHaloTW - 1) / kHaloTW;
+  const int force_tg = []{ const char* e = getenv("UWM_HALO_TG"); return e ? atoi(e) : 0; }();
+  const int force_bn = []{ const char* e = getenv("UWM_HALO_BN"); return e ? atoi(e) : 0; }();
+  for (int bn : bns) {
+    if (force_bn && bn != force_bn && s.cout_pad % force_bn == 0 && s.cout_pad > 64) continue;
+    for (int tg = 1; tg <= 8; tg <<= 1) {
+      if (2 * tg * bn > 512) break;                               // two TMEM accumulator sets
+      if (tg > 1 && tg > w8) break;                               // tile wider than the image
+      if (force_tg && tg != force_tg && force_tg <= w8 && 2 * force_tg * bn <= 512) continue;
+      const size_t a_stage = (size_t)cps * halo_plane_bytes(tg, kh, kw);
+      const size_t b_slice = ((size_t)bn * kc * 2 + 1023) & ~(size_t)1023;
+      const int n_tiles = s.cout_pad / bn;
+      const bool resident = (n_tiles == 1) && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
+      if (!resident && (tg > 2 || 2 * b_slice + 2 * a_stage > kBudget)) break;   // streamed kernels: TG 1, 2
+      if (kh == 4 && !resident) break;
+      const long long tiles = (long long)((s.w + kHaloTW * tg - 1) / (kHaloTW * tg)) * ((s.h + kHaloTH - 1) / kHaloTH) * s.n * n_tiles;
+      const long long waves = (tiles + sms - 1) / sms;
+      const double mmas = (double)tg * nk * (kc / 16);
+      const double tensor = mmas * std::max(32, bn / 2);
+      const double issue = 6.0 * (60.0 * a.chunks + 12.0 * nk + 3.0 * mmas);
+      const double a_bytes = (double)halo_npix(tg, kh, kw) * cin_total * 2;
+      const double b_bytes = resident ? 0.0 : (double)bn * nk * kc * 2;
+      const int a_stages_fit = (int)((kBudget - (resident ? (size_t)nk * b_slice : 2 * b_slice)) / a_stage);
+      const double shallow = a_stages_fit < 3 ? 1.25 : 1.0;        // two stages cannot hide the load latency
+      const double t_sm = waves * std::max(std::max(tensor, issue), (a_bytes + b_bytes) / 64.0) * shallow;
+      const double t_l2 = tiles * (a_bytes + b_bytes) / 6300.0;
+      const double cost = std::max(t_sm, t_l2);
+      if (cost < best.cost * 0.97) best = {bn, tg, resident, cost};
+    }
+  }
+  if (!best.bn) return fail(UWM_EINVAL, "halo conv: no tile fits shared memory (cin=%d cout=%d)", cin_total, s.cout_pad);
+  const int bn = best.bn, tg = best.tg;
+  L->kh = kh; L->kw = kw; L->kc = kc; L->tg = tg; L->resident = best.resident ? 1 : 0;
+  a.tiles_w = (s.w + kHaloTW * tg - 1) / (kHaloTW * tg);
+  a.tiles_h = (s.h + kHaloTH - 1) / kHaloTH;
+  const int m_tiles = a.tiles_w * a.tiles_h * s.n;
+  const int pw = halo_pw(tg, kw), npix = halo_npix(tg, kh, kw);
+  a.pw_magic = 65536u / (uint32_t)pw + 1u;
+  for (int p = 0; p < npix; ++p)
+    if ((int)(((uint32_t)p * a.pw_magic) >> 16) != p / pw) return fail(UWM_ESTATE, "halo conv: division magic failed for pw=%d", pw);
+  const size_t a_stage_bytes = (size_t)cps * halo_plane_bytes(tg, kh, kw);
+  a.block_n = bn;
+  a.n_tiles = s.cout_pad / bn;
+  a.cout = s.cout;
+  a.total_tiles = m_tiles * a.n_tiles;
+  a.div_ntiles = make_fastdiv(a.n_tiles);
+  a.div_tw = make_fastdiv(a.tiles_w);
+  a.div_th = make_fastdiv(a.tiles_h);
+  const unsigned grid = (unsigned)std::min(a.total_tiles, sms);
+  a.b_slice_bytes = ((uint32_t)bn * kc * 2u + 1023u) & ~1023u;
+  const size_t resident_bytes = (size_t)nk * a.b_slice_bytes;
+  if (best.resident) {
+    a.kpb = 1; a.b_stages = 1;
+    a.a_stages = (int)std::min<size_t>(kHaloMaxStages, (kBudget - resident_bytes) / a_stage_bytes);
+  } else {
+    // taps per weight stage: enough MMA work per barrier round trip (>= ~512 cycles) if it still fits 3 deep
+    const int mma_cycles = tg * (kc / 16) * std::max(32, bn / 2);
+    const size_t a_min = (size_t)std::min(3, std::max(2, a.chunks + 1)) * a_stage_bytes;
+    int kpb = 1;
+    for (int d = 1; d <= s.ntaps; ++d) {
+      if (s.ntaps % d) continue;
+      if (3 * (size_t)d * a.b_slice_bytes + a_min > kBudget) break;
+      kpb = d;
+      if (d * mma_cycles >= 512) break;
+    }
+    a.kpb = kpb;
+    const size_t b_stage = (size_t)kpb * a.b_slice_bytes;
+    const size_t a_keep = std::min(a_min, kBudget - 2 * b_stage);
+    a.b_stages = (int)std::max<size_t>(2, std::min<size_t>(8, (kBudget - a_keep) / b_stage));
+    a.a_stages = (int)std::max<size_t>(2, std::min<size_t>(kHaloMaxStages, (kBudget - a.b_stages * b_stage) / a_stage_bytes));
+  }
+  { const char* e = getenv("UWM_HALO_ASTAGES"); if (e && atoi(e) >= 2) a.a_stages = std::min(a.a_stages, atoi(e)); }
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)(tg * bn)) cols <<= 1;
+  a.tmem_cols = cols;
+  a.bias = s.bias;
+  a.res = static_cast<const __nv_bfloat16*>(s.res);
+  a.out = static_cast<__nv_bfloat16*>(s.out);
+  a.res_pitch = s.res_pitch; a.out_pitch = s.out_pitch;
+  a.relu = s.relu;
+  a.head = s.head; a.apply_sigmoid = s.apply_sigmoid;
+  a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
+  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("UWM_VERBOSE");
+    if (e && e[0] == '1')
+      fprintf(stderr, "halo conv %dx%dx%d cin=%d(+%d%s) cout=%d %dx%d: bn=%d tg=%d kc=%d chunks=%d tiles=%d grid=%u a_stages=%d (%zu B) %s kpb=%d b_stages=%d\n",
+              s.n, s.h, s.w, s.cin, s.cin2, s.up1 ? ",up" : "", s.cout, kh, kw, bn, tg, kc, a.chunks, a.total_tiles, grid,
+              a.a_stages, a_stage_bytes, best.resident ? "B resident" : "B streamed", a.kpb, a.b_stages); }
+  L->grid = grid;
+  const size_t b_total = best.resident ? resident_bytes : (size_t)a.b_stages * a.kpb * a.b_slice_bytes;
+  L->smem = 1024 + b_total + (size_t)a.a_stages * a_stage_bytes + 1024;
+
+  const CUtensorMapSwizzle sw = (kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (kc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                           : CU_TENSOR_MAP_SWIZZLE_32B;
+  const cuuint64_t ktot = (cuuint64_t)s.ntaps * cin_total;
+  cuuint64_t dims[2] = {ktot, (cuuint64_t)s.cout_pad};
+  cuuint64_t strides[1] = {ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = enc(&L->tm_wgt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims, strides, box,
+                   est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(wgt) -> %d (k=%llu cout=%d)", (int)r, (unsigned long long)ktot, s.cout_pad);
+  return UWM_OK;
+}
+
+static int build_conv_stream(const ConvSpec& s, ConvLaunch* L);
+
+// Kernel selection: k x k stride-1 'same' convs (and anything with a fused upsample/concat) go to the
+// halo-resident kernel; stride-2 and 1x1 convs (plain GEMM, nothing to share between taps) to conv_tc.
 static int build_conv(const ConvSpec& s, ConvLaunch* L) {
+  const bool fused = s.up1 || s.x2;
+  const bool same = (s.stride == 1 && s.h_out == s.h && s.w_out == s.w);
+  if (fused || (same && (s.ntaps == 9 || s.ntaps == 16) && halo_enabled())) return build_halo(s, L);
+  return build_conv_stream(s, L);
+}
+
+static int build_conv_stream(const ConvSpec& s, ConvLaunch* L) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (s.cin % 16) return fail(UWM_EINVAL, "conv: cin=%d must be a multiple of 16", s.cin);
@@ -160,6 +369,7 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   if (s.res && ((s.res_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.res) & 15)))
     return fail(UWM_EINVAL, "conv: residual base/pitch must be 16-byte aligned");
 
+  L->halo = 0;
   ConvKArgs& a = L->args;
   memset(&a, 0, sizeof(a));
   a.n_img = s.n; a.h_out = s.h_out; a.w_out = s.w_out;
@@ -257,12 +467,37 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   return UWM_OK;
 }
 
+// Instantiation table of conv_halo_kernel<KC, KH, KW, TG, RESIDENT>.  L == nullptr: raise the dynamic
+// shared-memory limit of every instantiation (once); otherwise launch the one matching L.
+static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
+#define UWM_HALO_CASE(KC, KH, KW, TG, RES)                                                                      \
+  if (!L) {                                                                                                     \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES>,                                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));                    \
+  } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES) {           \
+    conv_halo_kernel<KC, KH, KW, TG, RES><<<L->grid, kHaloThreads, L->smem, st>>>(L->tm_wgt, L->hargs);          \
+    return UWM_OK;                                                                                              \
+  }
+  UWM_HALO_CASE(16, 3, 3, 1, true) UWM_HALO_CASE(16, 3, 3, 2, true) UWM_HALO_CASE(16, 3, 3, 4, true) UWM_HALO_CASE(16, 3, 3, 8, true)
+  UWM_HALO_CASE(32, 3, 3, 1, true) UWM_HALO_CASE(32, 3, 3, 2, true) UWM_HALO_CASE(32, 3, 3, 4, true) UWM_HALO_CASE(32, 3, 3, 8, true)
+  UWM_HALO_CASE(64, 3, 3, 1, true) UWM_HALO_CASE(64, 3, 3, 2, true) UWM_HALO_CASE(64, 3, 3, 4, true)
+  UWM_HALO_CASE(16, 3, 3, 1, false) UWM_HALO_CASE(16, 3, 3, 2, false)
+  UWM_HALO_CASE(32, 3, 3, 1, false) UWM_HALO_CASE(32, 3, 3, 2, false)
+  UWM_HALO_CASE(64, 3, 3, 1, false) UWM_HALO_CASE(64, 3, 3, 2, false)
+  UWM_HALO_CASE(16, 4, 4, 1, true) UWM_HALO_CASE(16, 4, 4, 2, true) UWM_HALO_CASE(16, 4, 4, 4, true) UWM_HALO_CASE(16, 4, 4, 8, true)
+#undef UWM_HALO_CASE
+  if (!L) return UWM_OK;
+  return fail(UWM_ESTATE, "halo conv: no kernel instantiated for kc=%d %dx%d tg=%d resident=%d", L->kc, L->kh, L->kw,
+              L->tg, L->resident);
+}
+
 static int set_conv_attrs() {
   static bool done = false;
   if (done) return UWM_OK;
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  { int rc = halo_dispatch(nullptr, nullptr); if (rc) return rc; }
   done = true;
   return UWM_OK;
 }
@@ -270,6 +505,11 @@ static int set_conv_attrs() {
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
   int rc = set_conv_attrs();
   if (rc) return rc;
+  if (L.halo) {
+    rc = halo_dispatch(&L, st);
+    if (rc) return rc;
+    return post_launch("conv_halo_kernel", st);
+  }
   switch (L.args.kc) {
     case 64: conv_tc_kernel<64><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
     case 32: conv_tc_kernel<32><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
@@ -311,6 +551,28 @@ extern "C" int uwm_conv2d_nhwc_bf16(const void* d_x, int n, int h, int w, int ci
   s.out = d_y; s.out_pitch = y_pitch;
   ConvLaunch L;
   int rc = build_conv(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uwm_conv2d_upcat_nhwc_bf16(const void* d_x, int n, int h, int w, int c_x, int x_pitch, int upsample,
+                                          const void* d_skip, int c_skip, int skip_pitch, const void* d_wgt,
+                                          const float* d_bias, int cout, int kh, int kw, int pad, int relu,
+                                          void* d_y, int y_pitch, void* stream) {
+  if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_upcat: null pointer");
+  if (cout % 16) return fail(UWM_EINVAL, "conv2d_upcat: cout=%d must be a multiple of 16", cout);
+  if (kh * kw > kMaxTaps) return fail(UWM_EINVAL, "conv2d_upcat: %dx%d kernel unsupported", kh, kw);
+  if (2 * pad != kh - 1 || 2 * pad != kw - 1) return fail(UWM_EINVAL, "conv2d_upcat: needs 'same' padding");
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.cin = c_x; s.x_pitch = x_pitch; s.up1 = upsample ? 1 : 0;
+  s.h = upsample ? 2 * h : h; s.w = upsample ? 2 * w : w;
+  if (d_skip) { s.x2 = d_skip; s.cin2 = c_skip; s.x2_pitch = skip_pitch; }
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = cout; s.cout_pad = cout;
+  taps_rect(&s, kh, kw, pad);
+  s.stride = 1; s.h_out = s.h; s.w_out = s.w;
+  s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_halo(s, &L);
   if (rc) return rc;
   return launch_conv(L, static_cast<cudaStream_t>(stream));
 }
@@ -388,12 +650,13 @@ struct Buf {
 struct TRef {            // a [B,h,w,c] bf16 view: channels [c_off, c_off+c) of a pitch-wide buffer
   int buf = -1, c_off = 0, c = 0, pitch = 0, h = 0, w = 0;
 };
-enum OpType { OP_PREP, OP_CONV, OP_HEAD, OP_POOL, OP_UP };
+enum OpType { OP_PREP, OP_CONV, OP_HEAD, OP_POOL };
 struct Op {
   OpType type;
   std::string name;
-  TRef in, out, res;
-  bool has_res = false;
+  TRef in, in2, out, res;     // in2: second conv source (skip), concatenated after `in` along channels
+  bool has_res = false, has_in2 = false;
+  bool up = false;            // `in` is nearest-2x upsampled on the fly (decoder conv1)
   int layer = -1;
   double flops_per_img = 0, bytes_per_img = 0;
 };
@@ -474,17 +737,22 @@ static int add_layer(uwm_model* m, const std::string& conv_key, const std::strin
 }
 
 // conv op: output spatial size is derived from the layer's stride/pad
-static void add_conv(uwm_model* m, int layer, const TRef& in, const TRef& out, const TRef* res, bool head = false) {
+static void add_conv(uwm_model* m, int layer, const TRef& in, const TRef& out, const TRef* res, bool head = false,
+                     bool up = false, const TRef* in2 = nullptr, int out_h = 0, int out_w = 0) {
   Op op;
   op.type = head ? OP_HEAD : OP_CONV;
   const uwm_layer_desc& d = m->layers[layer].d;
   op.name = d.conv_key;
-  op.in = in; op.out = out; op.layer = layer;
+  op.in = in; op.out = out; op.layer = layer; op.up = up;
   if (res) { op.res = *res; op.has_res = true; }
-  const double px = (double)out.h * out.w;
+  if (in2) { op.in2 = *in2; op.has_in2 = true; }
+  if (head) { op.out.h = out_h; op.out.w = out_w; }
+  const double px = (double)op.out.h * op.out.w;
   op.flops_per_img = 2.0 * d.cin * d.cout * d.kh * d.kw * px;
-  const double in_px = m->layers[layer].stem ? (double)(in.h * 2) * (in.w * 2) : (double)in.h * in.w;
-  op.bytes_per_img = 2.0 * in_px * d.cin + (head ? 5.0 * px : 2.0 * px * d.cout) + (res ? 2.0 * px * d.cout : 0.0);
+  // algorithmic bytes: every source read once at its stored resolution, output written once
+  double in_bytes = m->layers[layer].stem ? 2.0 * in.h * in.w * 16 : 2.0 * (double)in.h * in.w * in.c;
+  if (in2) in_bytes += 2.0 * (double)in2->h * in2->w * in2->c;
+  op.bytes_per_img = in_bytes + (head ? 1.0 * px : 2.0 * px * d.cout) + (res ? 2.0 * px * d.cout : 0.0);
   m->layers[layer].d.flops_per_image = op.flops_per_img;
   m->flops_per_img += op.flops_per_img;
   m->ops.push_back(op);
@@ -507,20 +775,18 @@ static int build_plan(uwm_model* m) {
     if (dec[i] <= 0 || dec[i] % 16)
       return fail(UWM_EINVAL, "decoder_channels[%d]=%d: must be a positive multiple of 16", i, dec[i]);
 
-  // decoder concat buffers: block i consumes [ up(x_i) (cx ch) | skip (cs ch) ] at 1/2^(4-i) scale
+  // decoder block i consumes concat( up2x(x_i) [cx ch], skip_i [cs ch] ) at 1/2^(4-i) scale.  Neither the
+  // upsampled tensor nor the concat is materialised: conv1's loader reads x_i and skip_i directly.
   const int cx[5] = {enc_ch[4], dec[0], dec[1], dec[2], dec[3]};
   const int cs[5] = {enc_ch[3], enc_ch[2], enc_ch[1], enc_ch[0], 0};
-  TRef cat[5];
-  for (int i = 0; i < 5; ++i) cat[i] = m->dense(H >> (4 - i), W >> (4 - i), cx[i] + cs[i]);
-  auto skip_slot = [&](int i) {  // where encoder feature feeding decoder block i is written
-    TRef t = cat[i]; t.c_off = cx[i]; t.c = cs[i]; return t;
-  };
+  TRef skip[5];   // encoder feature feeding decoder block i (filled in as the encoder is laid out)
 
   // ---- input prep + stem ----
   TRef xs = m->dense(H / 2, W / 2, 16);
   { Op op; op.type = OP_PREP; op.name = "prep"; op.out = xs;
     op.bytes_per_img = 12.0 * H * W /*fp32 in (u8: 3)*/ + 2.0 * (H / 2) * (W / 2) * 16; m->ops.push_back(op); }
-  TRef f1 = skip_slot(3);   // stem output, 64 ch @ H/2
+  TRef f1 = m->dense(H / 2, W / 2, 64);   // stem output, 64 ch @ H/2
+  skip[3] = f1;
   int l = add_layer(m, "encoder.conv1", "encoder.bn1", 3, 64, 7, 2, 3, 1, 0, /*stem=*/true);
   add_conv(m, l, xs, f1, nullptr);
   m->named["encoder.stem"] = f1;
@@ -538,10 +804,8 @@ static int build_plan(uwm_model* m) {
       const int oh = cur_h / stride, ow = cur_w / stride;
       const std::string pre = fmt("encoder.layer%d.%d", li + 1, b);
       const bool last = (b == nblk[li] - 1);
-      TRef out;
-      if (last && li < 3) out = skip_slot(2 - li);        // layer1->cat[2], layer2->cat[1], layer3->cat[0]
-      else out = m->dense(oh, ow, out_c);
-      out.h = oh; out.w = ow;
+      TRef out = m->dense(oh, ow, out_c);
+      if (last && li < 3) skip[2 - li] = out;             // layer1 -> block 2, layer2 -> block 1, layer3 -> block 0
       TRef identity = x;
       const bool need_ds = (b == 0) && (stride != 1 || cur_c != out_c);
       if (need_ds) {
@@ -573,14 +837,12 @@ static int build_plan(uwm_model* m) {
 
   // ---- decoder ----
   for (int i = 0; i < 5; ++i) {
-    TRef up = cat[i]; up.c_off = 0; up.c = cx[i];
-    { Op op; op.type = OP_UP; op.name = fmt("decoder.blocks.%d.upsample", i); op.in = x; op.out = up;
-      op.bytes_per_img = 2.0 * cx[i] * ((double)x.h * x.w + (double)up.h * up.w); m->ops.push_back(op); }
+    const int bh = H >> (4 - i), bw = W >> (4 - i);
     const std::string pre = fmt("decoder.blocks.%d", i);
-    TRef t1 = m->dense(cat[i].h, cat[i].w, dec[i]);
+    TRef t1 = m->dense(bh, bw, dec[i]);
     int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0);
-    add_conv(m, l1, cat[i], t1, nullptr);
-    TRef t2 = m->dense(cat[i].h, cat[i].w, dec[i]);
+    add_conv(m, l1, x, t1, nullptr, false, /*up=*/true, cs[i] ? &skip[i] : nullptr);
+    TRef t2 = m->dense(bh, bw, dec[i]);
     int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0);
     add_conv(m, l2, t1, t2, nullptr);
     x = t2;
@@ -589,7 +851,7 @@ static int build_plan(uwm_model* m) {
   // ---- head ----
   int lh = add_layer(m, "segmentation_head.0", "", dec[4], 1, 3, 1, 1, 0, 0);
   TRef none;
-  add_conv(m, lh, x, none, nullptr, /*head=*/true);
+  add_conv(m, lh, x, none, nullptr, /*head=*/true, false, nullptr, H, W);
 
   // ---- liveness + arena offsets ----
   for (int i = 0; i < (int)m->ops.size(); ++i) {
@@ -597,6 +859,7 @@ static int build_plan(uwm_model* m) {
     if (op.in.buf >= 0) m->touch(op.in, i);
     if (op.out.buf >= 0) m->touch(op.out, i);
     if (op.has_res) m->touch(op.res, i);
+    if (op.has_in2) m->touch(op.in2, i);
   }
   std::vector<int> order;
   for (int i = 0; i < (int)m->bufs.size(); ++i) if (m->bufs[i].last >= 0) order.push_back(i);
@@ -699,7 +962,6 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
         L.src = d_in; L.dst = m->ptr(op.out); L.n = batch; L.h = m->H; L.w = m->W; L.c = in_fmt;
         break;
       case OP_POOL:
-      case OP_UP:
         L.src = m->ptr(op.in); L.dst = m->ptr(op.out); L.n = batch; L.h = op.in.h; L.w = op.in.w; L.c = op.in.c;
         L.src_pitch = op.in.pitch; L.dst_pitch = op.out.pitch;
         break;
@@ -716,10 +978,14 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
           for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { s.dh[r * 4 + c] = (int8_t)(r - 2); s.dw[r * 4 + c] = (int8_t)(c - 2); }
           s.h_out = op.in.h; s.w_out = op.in.w;
         } else {
-          s.cin = ly.d.cin; s.stride = ly.d.stride;
+          s.cin = op.in.c; s.stride = ly.d.stride;
+          if (op.up) { s.up1 = 1; s.h = op.in.h * 2; s.w = op.in.w * 2; }
+          if (op.has_in2) { s.x2 = m->ptr(op.in2); s.cin2 = op.in2.c; s.x2_pitch = op.in2.pitch; }
+          if (s.cin + s.cin2 != ly.d.cin)
+            return fail(UWM_ESTATE, "plan bug: %s reads %d+%d channels, layer has %d", ly.d.conv_key, s.cin, s.cin2, ly.d.cin);
           taps_rect(&s, ly.d.kh, ly.d.kw, ly.d.pad);
-          s.h_out = (op.in.h + 2 * ly.d.pad - ly.d.kh) / ly.d.stride + 1;
-          s.w_out = (op.in.w + 2 * ly.d.pad - ly.d.kw) / ly.d.stride + 1;
+          s.h_out = (s.h + 2 * ly.d.pad - ly.d.kh) / ly.d.stride + 1;
+          s.w_out = (s.w + 2 * ly.d.pad - ly.d.kw) / ly.d.stride + 1;
         }
         s.relu = ly.d.relu;
         if (op.type == OP_HEAD) {
@@ -744,7 +1010,6 @@ static int run_launch(const Launch& L, cudaStream_t st) {
   switch (L.type) {
     case OP_PREP: return launch_prep(L.src, L.c, L.n, L.h, L.w, L.dst, st);
     case OP_POOL: return launch_maxpool(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
-    case OP_UP: return launch_upsample(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
     case OP_CONV:
     case OP_HEAD: return launch_conv(L.conv, st);
   }
@@ -779,6 +1044,8 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
   first.src = d_in; first.c = in_fmt;
   last.conv.args.logits = d_logits; last.conv.args.mask = d_mask;
   last.conv.args.thr_logit = thr_logit; last.conv.args.apply_sigmoid = apply_sigmoid;
+  last.conv.hargs.logits = d_logits; last.conv.hargs.mask = d_mask;
+  last.conv.hargs.thr_logit = thr_logit; last.conv.hargs.apply_sigmoid = apply_sigmoid;
   const size_t n = pl.launches.size();
   if (!use_graph || debug_sync() || n < 3) {
     for (const Launch& L : pl.launches) { rc = run_launch(L, st); if (rc) return rc; }

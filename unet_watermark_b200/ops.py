@@ -53,6 +53,28 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, kh: int,
     return out
 
 
+def conv2d_upcat(x: torch.Tensor, skip: Optional[torch.Tensor], w_packed: torch.Tensor, bias: torch.Tensor,
+                 kh: int = 3, kw: int = 3, pad: int = 1, relu: bool = True, upsample: bool = True,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv(concat(nearest_up2x(x), skip)) (+bias)(+ReLU) in one kernel (smp DecoderBlock: interpolate+cat+conv1)."""
+    _require_cuda(x, skip, w_packed, bias, out)
+    lib = _lib.load()
+    n, h, w, cx = x.shape
+    cout = w_packed.shape[0]
+    ho, wo = (2 * h, 2 * w) if upsample else (h, w)
+    if skip is not None:
+        assert skip.shape[:3] == (n, ho, wo), (skip.shape, (n, ho, wo))
+    if out is None:
+        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_upcat_nhwc_bf16(
+        x.data_ptr(), n, h, w, cx, _pitch(x), int(upsample),
+        skip.data_ptr() if skip is not None else None, skip.shape[3] if skip is not None else 0,
+        _pitch(skip) if skip is not None else 0, w_packed.data_ptr(), bias.data_ptr(), cout, kh, kw, pad,
+        int(relu), out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_upcat_nhwc_bf16")
+    return out
+
+
 def head(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, threshold: Optional[float] = 0.5,
          thr_on_logits: bool = False, want_logits: bool = True, apply_sigmoid: bool = False):
     """conv3x3(Cin->1)+bias -> (fp32 logits [N,H,W] or None, uint8 mask [N,H,W] or None)."""
