@@ -33,6 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dbg", default="0")
     ap.add_argument("--filter", default="")
+    ap.add_argument("--graph", action="store_true", help="time 20 launches captured in one CUDA graph (no host launch cost)")
     args = ap.parse_args()
     dbgs = [int(v) for v in args.dbg.split(",")]
     dev = torch.device("cuda:0")
@@ -54,12 +55,25 @@ def main():
                 ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record()
-            for _ in range(10):
-                ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1) / 10)
+            if args.graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(20):
+                        ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+                g.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1) / 20)
+            else:
+                e0.record()
+                for _ in range(10):
+                    ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1) / 10)
         os.environ["UWM_DBG"] = "0"
         fl = 2.0 * n * ho * wo * cin * cout * 9
         by = 2.0 * (x.numel() + out.numel() + (skip.numel() if skip is not None else 0))

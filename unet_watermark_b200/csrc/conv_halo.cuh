@@ -179,6 +179,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
@@ -303,80 +304,91 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     }
   } else if (warp < kHaloLoaderWarp0) {
     // ------------------------------------------------------------ epilogue (4 warps)
+    // Per 16-column chunk the bias is loaded once and the TG sub-tiles are walked with the TMEM load of
+    // sub-tile g+1 in flight while sub-tile g is biased / ReLU'd / packed / stored.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;           // accumulator row == pixel of the 8x16 sub-tile
     const int wi = row & (kHaloTW - 1);
     const int hi = row >> 3;
+    const float lo_clamp = p.relu ? 0.f : -INFINITY;
+    const uint32_t bn = (uint32_t)p.block_n;
+    pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
       const int acc = it & 1;
       const HaloTile t = halo_decode<TG>(p, tile);
       const int oh = t.h0 + hi;
+      const int ow0 = t.w0 + wi;
       const int col0 = t.n_tile * p.block_n;
+      const bool row_ok = oh < p.h;
+      const long long pix0 = ((long long)t.img * p.h + oh) * p.w + ow0;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (TG * bn);
 
       if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> 1) & 1u);
       __syncwarp();
       tc_fence_after();
-#pragma unroll 1
-      for (int g = 0; g < TG; ++g) {
-        const int ow = t.w0 + g * kHaloTW + wi;
-        const bool valid = (ow < p.w) && (oh < p.h);
-        const long long pix = ((long long)t.img * p.h + oh) * p.w + ow;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * TG + g) * p.block_n);
 
-        if (p.dbg & 4) {
-          // bench-only: no epilogue work
-        } else if (p.head) {
-          uint32_t v[16];
-          tmem_ld_x16(taddr, v);
-          tmem_ld_wait();
-          if (valid) {
-            const float z = __uint_as_float(v[0]) + __ldg(p.bias);
-            if (p.logits) p.logits[pix] = p.apply_sigmoid ? 1.f / (1.f + __expf(-z)) : z;
-            if (p.mask) p.mask[pix] = (z > p.thr_logit) ? 255 : 0;
+      if (p.dbg & 4) {
+        // bench-only: no epilogue work
+      } else if (p.head) {
+        uint32_t z[TG];
+#pragma unroll
+        for (int g = 0; g < TG; ++g) tmem_ld_x1(taddr0 + g * bn, z[g]);
+        tmem_ld_wait();
+        const float b = __ldg(p.bias);
+#pragma unroll
+        for (int g = 0; g < TG; ++g) {
+          if (row_ok && ow0 + g * kHaloTW < p.w) {
+            const float zz = __uint_as_float(z[g]) + b;
+            if (p.logits) p.logits[pix0 + g * kHaloTW] = p.apply_sigmoid ? 1.f / (1.f + __expf(-zz)) : zz;
+            if (p.mask) p.mask[pix0 + g * kHaloTW] = (zz > p.thr_logit) ? 255 : 0;
           }
-        } else {
-          __nv_bfloat16* orow = p.out + pix * p.out_pitch + col0;
-          const __nv_bfloat16* rrow = p.res ? p.res + pix * p.res_pitch + col0 : nullptr;
-          const float4* brow = reinterpret_cast<const float4*>(p.bias + col0);
-          const int ncols = min(p.block_n, p.cout - col0);
-          for (int c = 0; c < ncols; c += 16) {
-            uint32_t v[16];
-            tmem_ld_x16(taddr + c, v);
-            const float4 b0 = __ldg(brow + (c >> 2)), b1 = __ldg(brow + (c >> 2) + 1);
-            const float4 b2 = __ldg(brow + (c >> 2) + 2), b3 = __ldg(brow + (c >> 2) + 3);
+        }
+      } else {
+        __nv_bfloat16* obase = p.out + pix0 * p.out_pitch + col0;
+        const __nv_bfloat16* rbase = p.res ? p.res + pix0 * p.res_pitch + col0 : nullptr;
+        const long long ostep = (long long)kHaloTW * p.out_pitch, rstep = (long long)kHaloTW * p.res_pitch;
+        const float4* brow = reinterpret_cast<const float4*>(p.bias + col0);
+        const int ncols = min(p.block_n, p.cout - col0);
+        for (int c = 0; c < ncols; c += 16) {
+          uint32_t v[2][16];
+          tmem_ld_x16(taddr0 + c, v[0]);
+          const float4 b0 = __ldg(brow + (c >> 2)), b1 = __ldg(brow + (c >> 2) + 1);
+          const float4 b2 = __ldg(brow + (c >> 2) + 2), b3 = __ldg(brow + (c >> 2) + 3);
+          const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
+                                b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+#pragma unroll
+          for (int g = 0; g < TG; ++g) {
+            const bool valid = row_ok && (ow0 + g * kHaloTW < p.w);
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-            if (rrow && valid) {
-              r0 = *reinterpret_cast<const uint4*>(rrow + c);
-              r1 = *reinterpret_cast<const uint4*>(rrow + c + 8);
+            if (rbase && valid) {
+              r0 = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
+              r1 = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
             }
             tmem_ld_wait();
+            if (g + 1 < TG) tmem_ld_x16(taddr0 + (g + 1) * bn + c, v[(g + 1) & 1]);
             if (valid) {
               float f[16];
-              const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
-                                    b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
-              if (rrow) {
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[g & 1][j]) + bb[j];
+              if (rbase) {
                 const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(rr[j]); f[2 * j + 1] += bf16_hi(rr[j]); }
               }
-              if (p.relu) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], lo_clamp);
               uint4 o0, o1;
               o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
               o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
               o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
               o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-              *reinterpret_cast<uint4*>(orow + c) = o0;
-              *reinterpret_cast<uint4*>(orow + c + 8) = o1;
+              *reinterpret_cast<uint4*>(obase + g * ostep + c) = o0;
+              *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;
             }
           }
         }
-      }  // sub-tiles
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar(acc));
@@ -384,6 +396,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   } else {
     // ------------------------------------------------------------ activation loaders (4 warps)
     const int lt = threadIdx.x - kHaloLoaderWarp0 * 32;
+    pdl_wait();                              // activations are written by the previous kernel
     int s = 0; uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
       const HaloTile t = halo_decode<TG>(p, tile);

@@ -106,6 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 4); }
@@ -122,6 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_slot;
+  pdl_wait();                                // everything below reads / writes activations of the previous kernel
 
   const int G = gridDim.x;
 

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx_sm100.cuh"
+
 namespace uwm {
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -24,6 +26,8 @@ template <bool kU8>
 __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ in,
                                                        __nv_bfloat16* __restrict__ out, int n,
                                                        int h, int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h2 = h >> 1, w2 = w >> 1;
   const long long total = (long long)n * h2 * w2;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ y, int n,
                                                            int h, int w, int c, long long x_pitch,
                                                            long long y_pitch) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ho = h >> 1, wo = w >> 1, cg = c >> 3;
   const long long total = (long long)n * ho * wo * cg;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -129,6 +135,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
                                                          __nv_bfloat16* __restrict__ y, int n,
                                                          int h, int w, int c, long long x_pitch,
                                                          long long y_pitch) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ho = h * 2, wo = w * 2, cg = c >> 3;
   const long long total = (long long)n * ho * wo * cg;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;

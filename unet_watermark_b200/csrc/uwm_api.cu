@@ -88,6 +88,24 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in the
+// stream drains; every kernel here calls griddepcontrol.wait before touching dependent memory.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UWM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -293,7 +311,9 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   } else {
     // taps per weight stage: enough MMA work per barrier round trip (>= ~512 cycles) if it still fits 3 deep
     const int mma_cycles = tg * (kc / 16) * std::max(32, bn / 2);
-    const size_t a_min = (size_t)std::min(3, std::max(2, a.chunks + 1)) * a_stage_bytes;
+    // an activation stage lasts all taps of a chunk (thousands of cycles): two are enough; the short-lived
+    // weight stages get the rest of shared memory so the ring covers the L2 latency under load
+    const size_t a_min = 2 * a_stage_bytes;
     int kpb = 1;
     for (int d = 1; d <= s.ntaps; ++d) {
       if (s.ntaps % d) continue;
@@ -304,7 +324,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     a.kpb = kpb;
     const size_t b_stage = (size_t)kpb * a.b_slice_bytes;
     const size_t a_keep = std::min(a_min, kBudget - 2 * b_stage);
-    a.b_stages = (int)std::max<size_t>(2, std::min<size_t>(8, (kBudget - a_keep) / b_stage));
+    a.b_stages = (int)std::max<size_t>(2, std::min<size_t>(12, (kBudget - a_keep) / b_stage));
     a.a_stages = (int)std::max<size_t>(2, std::min<size_t>(kHaloMaxStages, (kBudget - a.b_stages * b_stage) / a_stage_bytes));
   }
   { const char* e = getenv("UWM_HALO_ASTAGES"); if (e && atoi(e) >= 2) a.a_stages = std::min(a.a_stages, atoi(e)); }
@@ -475,7 +495,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES>,                                        \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));                    \
   } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES) {           \
-    conv_halo_kernel<KC, KH, KW, TG, RES><<<L->grid, kHaloThreads, L->smem, st>>>(L->tm_wgt, L->hargs);          \
+    launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->hargs);     \
     return UWM_OK;                                                                                              \
   }
   UWM_HALO_CASE(16, 3, 3, 1, true) UWM_HALO_CASE(16, 3, 3, 2, true) UWM_HALO_CASE(16, 3, 3, 4, true) UWM_HALO_CASE(16, 3, 3, 8, true)
@@ -511,9 +531,9 @@ static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
     return post_launch("conv_halo_kernel", st);
   }
   switch (L.args.kc) {
-    case 64: conv_tc_kernel<64><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
-    case 32: conv_tc_kernel<32><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
-    default: conv_tc_kernel<16><<<L.grid, kConvThreads, L.smem, st>>>(L.tm_act, L.tm_wgt, L.args); break;
+    case 64: launch_pdl(conv_tc_kernel<64>, L.grid, kConvThreads, L.smem, st, L.tm_act, L.tm_wgt, L.args); break;
+    case 32: launch_pdl(conv_tc_kernel<32>, L.grid, kConvThreads, L.smem, st, L.tm_act, L.tm_wgt, L.args); break;
+    default: launch_pdl(conv_tc_kernel<16>, L.grid, kConvThreads, L.smem, st, L.tm_act, L.tm_wgt, L.args); break;
   }
   return post_launch("conv_tc_kernel", st);
 }
@@ -597,16 +617,16 @@ static int launch_maxpool(const void* x, int n, int h, int w, int c, long long x
                           cudaStream_t st) {
   if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
   const long long items = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool3x3s2_kernel<<<stream_grid(items, 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
+  launch_pdl(maxpool3x3s2_kernel, stream_grid(items, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(x),
+             static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
   return post_launch("maxpool3x3s2_kernel", st);
 }
 static int launch_upsample(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
                            cudaStream_t st) {
   if (c % 8) return fail(UWM_EINVAL, "upsample: c%%8 must be 0");
   const long long items = (long long)n * (h * 2) * (w * 2) * (c / 8);
-  upsample2x_kernel<<<stream_grid(items, 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
+  launch_pdl(upsample2x_kernel, stream_grid(items, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(x),
+             static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
   return post_launch("upsample2x_kernel", st);
 }
 static int launch_prep(const void* in, int fmt, int n, int h, int w, void* y, cudaStream_t st) {
@@ -614,9 +634,9 @@ static int launch_prep(const void* in, int fmt, int n, int h, int w, void* y, cu
   const long long items = (long long)n * (h / 2) * (w / 2);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
   if (fmt == UWM_IN_U8_NHWC)
-    prep_s2d_kernel<true><<<stream_grid(items, 256), 256, 0, st>>>(in, out, n, h, w);
+    launch_pdl(prep_s2d_kernel<true>, stream_grid(items, 256), 256, 0, st, in, out, n, h, w);
   else if (fmt == UWM_IN_F32_NCHW)
-    prep_s2d_kernel<false><<<stream_grid(items, 256), 256, 0, st>>>(in, out, n, h, w);
+    launch_pdl(prep_s2d_kernel<false>, stream_grid(items, 256), 256, 0, st, in, out, n, h, w);
   else
     return fail(UWM_EINVAL, "prep: unknown input format %d", fmt);
   return post_launch("prep_s2d_kernel", st);
@@ -674,9 +694,16 @@ struct Launch {          // one kernel of an instantiated plan
   int n = 0, h = 0, w = 0, c = 0;
   long long src_pitch = 0, dst_pitch = 0;
 };
-struct Plan {            // launches of one forward at a fixed batch size (+ the captured body graph)
+struct GraphKey {        // caller-owned arguments baked into a captured forward
+  const void* in; const void* logits; const void* mask; int in_fmt, apply_sigmoid; uint32_t thr_bits;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(in, logits, mask, in_fmt, apply_sigmoid, thr_bits) <
+           std::tie(o.in, o.logits, o.mask, o.in_fmt, o.apply_sigmoid, o.thr_bits);
+  }
+};
+struct Plan {            // launches of one forward at a fixed batch size (+ the captured graphs)
   std::vector<Launch> launches;
-  cudaGraphExec_t body = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
 };
 
 }  // namespace
@@ -918,7 +945,7 @@ extern "C" int uwm_model_create(int encoder, const int* decoder_channels, int h,
 
 extern "C" int uwm_model_destroy(uwm_model* m) {
   if (!m) return UWM_OK;
-  for (auto& kv : m->plans) if (kv.second.body) cudaGraphExecDestroy(kv.second.body);
+  for (auto& kv : m->plans) for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
   for (auto& L : m->layers) { if (L.d_w) cudaFree(L.d_w); if (L.d_b) cudaFree(L.d_b); }
   if (m->arena) cudaFree(m->arena);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
@@ -1031,8 +1058,8 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto pit = m->plans.find(batch);
   if (pit == m->plans.end()) {
-    // tensor maps and tile shapes depend on the batch only; pointers of the first (prep) and last
-    // (head) kernels are patched per call, so the cached plan and its graph are reusable.
+    // tensor maps and tile shapes depend on the batch only; the caller-owned pointers of the first (prep)
+    // and last (head) kernels are patched per call
     Plan pl;
     rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &pl.launches);
     if (rc) return rc;
@@ -1047,31 +1074,39 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
   last.conv.hargs.logits = d_logits; last.conv.hargs.mask = d_mask;
   last.conv.hargs.thr_logit = thr_logit; last.conv.hargs.apply_sigmoid = apply_sigmoid;
   const size_t n = pl.launches.size();
-  if (!use_graph || debug_sync() || n < 3) {
+  if (!use_graph || debug_sync()) {
     for (const Launch& L : pl.launches) { rc = run_launch(L, st); if (rc) return rc; }
     return UWM_OK;
   }
-  if (!pl.body) {
-    // capture everything between prep and head (all pointers library-owned) once per batch size
+  // One CUDA graph per distinct argument set (input / output pointers, threshold, activation): the whole
+  // forward, prep to head, is a single graph launch whose kernel-to-kernel edges are programmatic (PDL).
+  uint32_t thr_bits; memcpy(&thr_bits, &thr_logit, 4);
+  const GraphKey key{d_in, d_logits, d_mask, in_fmt, apply_sigmoid, thr_bits};
+  auto git = pl.graphs.find(key);
+  if (git == pl.graphs.end()) {
+    if (pl.graphs.size() >= 64) {          // callers that rotate through unbounded pointer sets: start over
+      for (auto& kv : pl.graphs) cudaGraphExecDestroy(kv.second);
+      pl.graphs.clear();
+    }
     rc = set_conv_attrs();
     if (rc) return rc;
     cudaGraph_t g = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed));
-    for (size_t i = 1; i + 1 < n; ++i) {
+    for (size_t i = 0; i < n; ++i) {
       rc = run_launch(pl.launches[i], m->cap_stream);
       if (rc) { cudaStreamEndCapture(m->cap_stream, &g); if (g) cudaGraphDestroy(g); return rc; }
     }
     CUDA_TRY(cudaStreamEndCapture(m->cap_stream, &g));
-    cudaError_t e = cudaGraphInstantiate(&pl.body, g, 0);
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
     cudaGraphDestroy(g);
-    if (e != cudaSuccess) { pl.body = nullptr; return fail(UWM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
-    g_launches.fetch_sub(n - 2, std::memory_order_relaxed);   // capture is not execution
+    if (e != cudaSuccess) return fail(UWM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_sub(n, std::memory_order_relaxed);   // capture is not execution
+    git = pl.graphs.emplace(key, exec).first;
   }
-  rc = run_launch(first, st);
-  if (rc) return rc;
-  CUDA_TRY(cudaGraphLaunch(pl.body, st));
-  g_launches.fetch_add(n - 2, std::memory_order_relaxed);
-  return run_launch(last, st);
+  CUDA_TRY(cudaGraphLaunch(git->second, st));
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  return UWM_OK;
 }
 
 __global__ void gather_pitched_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
