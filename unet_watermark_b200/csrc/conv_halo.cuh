@@ -27,16 +27,19 @@
 // instructions per tile in a generic loop), so its loop is fully unrolled with immediate descriptor offsets
 // and TG sub-tiles share every wait/commit.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0    weight TMA producer          warp 1    TMEM owner + tcgen05.mma issuer
-//   warps 2-5 epilogue (TMEM -> bias/residual/ReLU -> bf16 NHWC, or head: logits / uint8 mask)
-//   warps 6-9 activation loaders
+// Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      weight TMA producer          warp 1    TMEM owner + tcgen05.mma issuer
+//   warps 2-5   epilogue set 0 (TMEM -> bias/residual/ReLU -> bf16 NHWC, or head: logits / uint8 mask)
+//   warps 6-9   activation loaders
+//   warps 10-13 epilogue set 1: a warp may only read TMEM lanes 32*(warp%4).., and one warp per lane quarter
+//               is latency-bound (one TMEM load -> math -> store chain at a time), so every quarter gets two
+//               warps that split the sub-tiles (or the 16-column chunks when TG == 1) of each tile
 #pragma once
 #include "conv_tc.cuh"
 
 namespace uwm {
 
-constexpr int kHaloThreads = 320;
+constexpr int kHaloThreads = 448;
 constexpr int kHaloLoaderThreads = 128;
 constexpr int kHaloLoaderWarp0 = 6;
 constexpr int kHaloTW = 8, kHaloTH = 16;
@@ -183,7 +186,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
     mbar_init(bres_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
@@ -302,8 +305,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         umma_commit(accf_bar(acc));
       }
     }
-  } else if (warp < kHaloLoaderWarp0) {
-    // ------------------------------------------------------------ epilogue (4 warps)
+  } else if (warp < kHaloLoaderWarp0 || warp >= kHaloLoaderWarp0 + 4) {
+    // ------------------------------------------------------------ epilogue (2 x 4 warps)
     // Per 16-column chunk the bias is loaded once and the TG sub-tiles are walked with the TMEM load of
     // sub-tile g+1 in flight while sub-tile g is biased / ReLU'd / packed / stored.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
@@ -312,6 +315,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const int hi = row >> 3;
     const float lo_clamp = p.relu ? 0.f : -INFINITY;
     const uint32_t bn = (uint32_t)p.block_n;
+    const int eset = (warp >= kHaloLoaderWarp0) ? 1 : 0;       // which of the two warps of this lane quarter
+    constexpr int GN = (TG >= 2) ? TG / 2 : 1;                 // sub-tiles per warp: g = GSTEP*gi + g_first
+    constexpr int GSTEP = (TG >= 2) ? 2 : 1;
+    const int g_first = (TG >= 2) ? eset : 0;
+    const int c_first = (TG >= 2) ? 0 : 16 * eset, c_step = (TG >= 2) ? 16 : 32;
     pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
@@ -331,17 +339,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       if (p.dbg & 4) {
         // bench-only: no epilogue work
       } else if (p.head) {
-        uint32_t z[TG];
+        if (TG >= 2 || eset == 0) {
+          uint32_t z[GN];
 #pragma unroll
-        for (int g = 0; g < TG; ++g) tmem_ld_x1(taddr0 + g * bn, z[g]);
-        tmem_ld_wait();
-        const float b = __ldg(p.bias);
+          for (int gi = 0; gi < GN; ++gi) tmem_ld_x1(taddr0 + (uint32_t)(GSTEP * gi + g_first) * bn, z[gi]);
+          tmem_ld_wait();
+          const float b = __ldg(p.bias);
 #pragma unroll
-        for (int g = 0; g < TG; ++g) {
-          if (row_ok && ow0 + g * kHaloTW < p.w) {
-            const float zz = __uint_as_float(z[g]) + b;
-            if (p.logits) p.logits[pix0 + g * kHaloTW] = p.apply_sigmoid ? 1.f / (1.f + __expf(-zz)) : zz;
-            if (p.mask) p.mask[pix0 + g * kHaloTW] = (zz > p.thr_logit) ? 255 : 0;
+          for (int gi = 0; gi < GN; ++gi) {
+            const int g = GSTEP * gi + g_first;
+            if (row_ok && ow0 + g * kHaloTW < p.w) {
+              const float zz = __uint_as_float(z[gi]) + b;
+              if (p.logits) p.logits[pix0 + g * kHaloTW] = p.apply_sigmoid ? 1.f / (1.f + __expf(-zz)) : zz;
+              if (p.mask) p.mask[pix0 + g * kHaloTW] = (zz > p.thr_logit) ? 255 : 0;
+            }
           }
         }
       } else {
@@ -350,29 +361,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         const long long ostep = (long long)kHaloTW * p.out_pitch, rstep = (long long)kHaloTW * p.res_pitch;
         const float4* brow = reinterpret_cast<const float4*>(p.bias + col0);
         const int ncols = min(p.block_n, p.cout - col0);
-        for (int c = 0; c < ncols; c += 16) {
+        for (int c = c_first; c < ncols; c += c_step) {
           uint32_t v[2][16];
-          tmem_ld_x16(taddr0 + c, v[0]);
+          uint4 r0[2], r1[2];
+          auto res_load = [&](int g, uint4& a, uint4& b) {     // residual of sub-tile g, requested one step ahead
+            a = make_uint4(0, 0, 0, 0); b = make_uint4(0, 0, 0, 0);
+            if (rbase && row_ok && (ow0 + g * kHaloTW < p.w)) {
+              a = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
+              b = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
+            }
+          };
+          tmem_ld_x16(taddr0 + (uint32_t)g_first * bn + c, v[0]);
+          res_load(g_first, r0[0], r1[0]);
           const float4 b0 = __ldg(brow + (c >> 2)), b1 = __ldg(brow + (c >> 2) + 1);
           const float4 b2 = __ldg(brow + (c >> 2) + 2), b3 = __ldg(brow + (c >> 2) + 3);
           const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
                                 b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
-          for (int g = 0; g < TG; ++g) {
+          for (int gi = 0; gi < GN; ++gi) {
+            const int g = GSTEP * gi + g_first;
             const bool valid = row_ok && (ow0 + g * kHaloTW < p.w);
-            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-            if (rbase && valid) {
-              r0 = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
-              r1 = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
-            }
             tmem_ld_wait();
-            if (g + 1 < TG) tmem_ld_x16(taddr0 + (g + 1) * bn + c, v[(g + 1) & 1]);
+            if (gi + 1 < GN) {
+              tmem_ld_x16(taddr0 + (uint32_t)(g + GSTEP) * bn + c, v[(gi + 1) & 1]);
+              res_load(g + GSTEP, r0[(gi + 1) & 1], r1[(gi + 1) & 1]);
+            }
             if (valid) {
               float f[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[g & 1][j]) + bb[j];
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[gi & 1][j]) + bb[j];
               if (rbase) {
-                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                const uint4 x0 = r0[gi & 1], x1 = r1[gi & 1];
+                const uint32_t rr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(rr[j]); f[2 * j + 1] += bf16_hi(rr[j]); }
               }
