@@ -164,6 +164,10 @@ int    uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int batch,
 int    uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int blocks, long long* d_cycles,
                           void* stream);
 
+/* Bench-only: when non-NULL, CTA 0 of every halo conv launched afterwards writes clock64() stamps of its pipeline
+ * events into d_trace[0..600) (tools/gpu_trace.py decodes them).  NULL switches tracing off. */
+int    uwm_debug_set_trace(long long* d_trace);
+
 /* Sizing micro-benchmark: mbarrier ping-pong between two warps, cycles for `iters` round trips. */
 int    uwm_debug_handshake(int iters, int variant, int blocks, long long* d_cycles, void* stream);
 

@@ -1,0 +1,69 @@
+"""Timeline of CTA 0 of one halo conv launch (clock64 stamps written by the kernel, bench-only).
+
+    python tools/gpu_trace.py --filter layer1
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools.gpu_conv_bench import SHAPES  # noqa: E402
+from unet_watermark_b200 import _lib, ops, packing  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--filter", default="layer1")
+    ap.add_argument("--residual", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    for name, n, h, w, cx, cs, cout, up in SHAPES:
+        if args.filter not in name:
+            continue
+        x = torch.randn(n, h, w, cx, device=dev).to(torch.bfloat16)
+        ho, wo = (2 * h, 2 * w) if up else (h, w)
+        skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
+        cin = cx + cs
+        wp = packing.pack_taps(torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5)
+        b = torch.zeros(cout, device=dev)
+        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+        res = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16) if args.residual else None
+
+        def run():
+            if res is not None and not up and skip is None:
+                ops.conv2d(x, wp, b, 3, 3, 1, 1, relu=True, residual=res, out=out)
+            else:
+                ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        tr = torch.zeros(600, dtype=torch.int64, device=dev)
+        _lib.check(lib.uwm_debug_set_trace(tr.data_ptr()))
+        run()
+        torch.cuda.synchronize()
+        _lib.check(lib.uwm_debug_set_trace(None))
+        t = tr.cpu().tolist()
+        t0 = t[0]
+        rel = lambda v: (v - t0) if v else None  # noqa: E731
+        print(f"== {name}  (cycles since kernel start of CTA 0)")
+        print(f"prologue done {rel(t[1])}")
+        print("loader  stage: slot-free / copies-issued")
+        for i in range(72):
+            if t[16 + 2 * i]:
+                print(f"   {i:3d}: {rel(t[16 + 2 * i]):8d} {rel(t[17 + 2 * i]):8d}")
+        print("mma     tile: acc-free / first-stage-landed / issued   |  epilogue: acc-full / stored")
+        for i in range(80):
+            if t[160 + 3 * i]:
+                e0, e1 = rel(t[400 + 2 * i]), rel(t[401 + 2 * i])
+                print(f"   {i:3d}: {rel(t[160 + 3 * i]):8d} {rel(t[161 + 3 * i]):8d} {rel(t[162 + 3 * i]):8d}   | {e0} {e1}")
+        print("epilogue warp 2, tile 1, per batch of 4 items: loads issued / after wait::ld / batch stored")
+        for i in range(24):
+            if t[500 + 4 * i]:
+                print("   %3d: %s" % (i, " ".join(str(rel(t[500 + 4 * i + k])) for k in range(3))))
+
+
+if __name__ == "__main__":
+    main()

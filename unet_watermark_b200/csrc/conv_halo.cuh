@@ -94,6 +94,9 @@ struct HaloKArgs {
   float* logits;
   uint8_t* mask;
   float thr_logit;
+  int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
+  int bias_smem;                            // bias of all n_tiles*block_n channels staged in smem (<= 1024 channels)
+  long long* trace;                         // bench-only: CTA 0 writes clock64() stamps of its pipeline events (tools/gpu_trace.py)
   int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
 };
 
@@ -132,6 +135,13 @@ __device__ __forceinline__ void umma_halo(uint32_t tmem_d, uint32_t a_lo, uint32
   }
 }
 
+// trace slots (CTA 0 only): [0] kernel start, [1] prologue done, loaders 16+2*stage+{0 slot free, 1 copies issued},
+// MMA 160+3*tile+{0 accumulator free, 1 first stage landed, 2 all MMAs issued}, epilogue 400+2*tile+{0 accumulator
+// full, 1 tile stored}
+__device__ __forceinline__ void halo_trace(const HaloKArgs& p, int slot) {
+  if (p.trace && blockIdx.x == 0 && slot < 600) p.trace[slot] = clock64();
+}
+
 struct HaloTile { int n_tile, w0, h0, img; };
 template <int TG>
 __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
@@ -147,7 +157,8 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 
 template <int KC, int KH, int KW, int TG, bool RESIDENT>
 __global__ void __launch_bounds__(kHaloThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ HaloKArgs p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
+                 const __grid_constant__ HaloKArgs p) {
   constexpr int NT = KH * KW;
   constexpr int CPS = KC / 8;                               // 8-channel planes per stage
   constexpr int LOG2_CPS = (KC == 64) ? 3 : (KC == 32) ? 2 : 1;
@@ -168,8 +179,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   const uint32_t b_bytes_total = RESIDENT ? (uint32_t)nk * p.b_slice_bytes : (uint32_t)p.b_stages * b_stage_bytes;
   const uint32_t b_base = smem_base;
   const uint32_t a_base = smem_base + b_bytes_total;
-  const uint32_t misc_off = b_bytes_total + (uint32_t)p.a_stages * A_STAGE_BYTES;
-  const uint32_t bar_base = (smem_base + misc_off + 7u) & ~7u;
+  const uint32_t stg_base = (a_base + (uint32_t)p.a_stages * A_STAGE_BYTES + 1023u) & ~1023u;   // epilogue staging
+  const uint32_t stg_bytes = p.ep_tma ? 8u * 32u * 128u : 0u;
+  const uint32_t bar_base = (stg_base + stg_bytes + 7u) & ~7u;
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (kHaloMaxStages + s); };
   auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxStages + s); };
@@ -178,11 +190,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   auto acce_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + 2 + a); };
   const uint32_t bres_bar = bar_base + 8u * (4 * kHaloMaxStages + 4);
   uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 6));
+  // folded-BN bias of every output channel, staged once: the epilogue re-reads it per 16-column chunk, and the
+  // trace showed that re-read missing L1 (an L2 round trip of 500-800 cycles in front of the first FADD)
+  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 8));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0) halo_trace(p, 0);
+  if (p.bias_smem)
+    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += kHaloThreads) s_bias[i] = __ldg(p.bias + i);
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
@@ -190,6 +208,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     mbar_init(bres_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
+    if (p.ep_tma) tma_prefetch_desc(&tm_out);
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(s_tmem_slot), p.tmem_cols);
@@ -200,6 +219,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_slot;
   const int G = gridDim.x;
+  if (threadIdx.x == 0) halo_trace(p, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight TMA producer
@@ -257,8 +277,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         const uint32_t tmem_acc = tmem_base + (uint32_t)acc * (TG * bn);
         mbar_wait_fast(acce_bar(acc), ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        halo_trace(p, 160 + 3 * it);
         for (int ch = 0; ch < p.chunks; ++ch) {
           mbar_wait_fast(afull_bar(sa), pha);
+          if (ch == 0) halo_trace(p, 161 + 3 * it);
           fence_proxy_async_smem();        // loaders wrote through the generic proxy (cp.async)
           tc_fence_after();
           const uint32_t a_st = a_lo0 + (uint32_t)sa * a_stage_units;
@@ -303,6 +325,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
         umma_commit(accf_bar(acc));
+        halo_trace(p, 162 + 3 * it);
       }
     }
   } else if (warp < kHaloLoaderWarp0 || warp >= kHaloLoaderWarp0 + 4) {
@@ -320,6 +343,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     constexpr int GSTEP = (TG >= 2) ? 2 : 1;
     const int g_first = (TG >= 2) ? eset : 0;
     const int c_first = (TG >= 2) ? 0 : 16 * eset, c_step = (TG >= 2) ? 16 : 32;
+    const bool tma_out = p.ep_tma != 0;
+    const int ewarp = (warp & 3) + 4 * eset;                                  // 0..7
+    const uint32_t stg = stg_base + (uint32_t)ewarp * (32u * 128u);           // one 32-row x 128-byte buffer per warp
+    // 128B swizzle of the 16-byte chunks of this lane's row: chunk index ^ (row & 7)
+    const uint32_t my_row_off = (uint32_t)lane * 128u;
+    const uint32_t sw_xor = (uint32_t)lane & 7u;
     pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
@@ -335,6 +364,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> 1) & 1u);
       __syncwarp();
       tc_fence_after();
+      if (warp == 2 && lane == 0) halo_trace(p, 400 + 2 * it);
 
       if (p.dbg & 4) {
         // bench-only: no epilogue work
@@ -361,50 +391,84 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         const long long ostep = (long long)kHaloTW * p.out_pitch, rstep = (long long)kHaloTW * p.res_pitch;
         const float4* brow = reinterpret_cast<const float4*>(p.bias + col0);
         const int ncols = min(p.block_n, p.cout - col0);
-        for (int c = c_first; c < ncols; c += c_step) {
+        // Items: 16-column chunk j of column group cg (ep_cols = 16 or 64 columns) of sub-tile g.  The TMEM load
+        // of the next item and its residual are in flight while the current one is biased / ReLU'd / packed.
+        // ep_tma: the packed rows go to this warp's swizzled smem staging buffer and one lane issues a TMA tensor
+        // store per (sub-tile, 64-column group); otherwise each lane stores its pixel's 32 bytes directly.
+        const int log2_jn = (p.ep_cols == 64) ? 2 : 0;                    // chunks per column group: 4 or 1
+        const int jn = 1 << log2_jn;
+        const int NIT = GN << log2_jn;                                    // items per column group for this warp
+        for (int cg0 = c_first * jn; cg0 < ncols; cg0 += c_step * jn) {  // first column of the group
           uint32_t v[2][16];
           uint4 r0[2], r1[2];
-          auto res_load = [&](int g, uint4& a, uint4& b) {     // residual of sub-tile g, requested one step ahead
-            a = make_uint4(0, 0, 0, 0); b = make_uint4(0, 0, 0, 0);
+          auto item_load = [&](int n, int b) {
+            const int g = GSTEP * (n >> log2_jn) + g_first, c = cg0 + ((n & (jn - 1)) << 4);
+            tmem_ld_x16(taddr0 + (uint32_t)g * bn + c, v[b]);
+            r0[b] = make_uint4(0, 0, 0, 0); r1[b] = make_uint4(0, 0, 0, 0);
             if (rbase && row_ok && (ow0 + g * kHaloTW < p.w)) {
-              a = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
-              b = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
+              r0[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
+              r1[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
             }
           };
-          tmem_ld_x16(taddr0 + (uint32_t)g_first * bn + c, v[0]);
-          res_load(g_first, r0[0], r1[0]);
-          const float4 b0 = __ldg(brow + (c >> 2)), b1 = __ldg(brow + (c >> 2) + 1);
-          const float4 b2 = __ldg(brow + (c >> 2) + 2), b3 = __ldg(brow + (c >> 2) + 3);
-          const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
-                                b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+          item_load(0, 0);
+          for (int n0 = 0; n0 < NIT; n0 += 2) {
 #pragma unroll
-          for (int gi = 0; gi < GN; ++gi) {
-            const int g = GSTEP * gi + g_first;
-            const bool valid = row_ok && (ow0 + g * kHaloTW < p.w);
-            tmem_ld_wait();
-            if (gi + 1 < GN) {
-              tmem_ld_x16(taddr0 + (uint32_t)(g + GSTEP) * bn + c, v[(gi + 1) & 1]);
-              res_load(g + GSTEP, r0[(gi + 1) & 1], r1[(gi + 1) & 1]);
-            }
-            if (valid) {
-              float f[16];
+            for (int u = 0; u < 2; ++u) {
+              const int n = n0 + u;
+              if (n < NIT) {
+                const int j = n & (jn - 1);
+                const int g = GSTEP * (n >> log2_jn) + g_first, c = cg0 + (j << 4);
+                const bool valid = row_ok && (ow0 + g * kHaloTW < p.w);
+                float4 b0, b1, b2, b3;
+                if (p.bias_smem) {
+                  const float4* sb = reinterpret_cast<const float4*>(s_bias + col0 + c);
+                  b0 = sb[0]; b1 = sb[1]; b2 = sb[2]; b3 = sb[3];
+                } else {
+                  b0 = __ldg(brow + (c >> 2)); b1 = __ldg(brow + (c >> 2) + 1);
+                  b2 = __ldg(brow + (c >> 2) + 2); b3 = __ldg(brow + (c >> 2) + 3);
+                }
+                const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
+                                      b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+                tmem_ld_wait();
+                if (n + 1 < NIT) item_load(n + 1, (u + 1) & 1);
+                if (valid || tma_out) {
+                  float f[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[gi & 1][j]) + bb[j];
-              if (rbase) {
-                const uint4 x0 = r0[gi & 1], x1 = r1[gi & 1];
-                const uint32_t rr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                  for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[u][k]) + bb[k];
+                  if (rbase) {
+                    const uint32_t rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(rr[j]); f[2 * j + 1] += bf16_hi(rr[j]); }
+                    for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(rr[k]); f[2 * k + 1] += bf16_hi(rr[k]); }
+                  }
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], lo_clamp);
+                  uint4 o0, o1;
+                  o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                  o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                  o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                  o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                  if (tma_out) {
+                    if (j == 0) {          // the previous store of this warp must have read the buffer out
+                      if (lane == 0) bulk_wait_read<0>();
+                      __syncwarp();
+                    }
+                    st_shared_v4(stg + my_row_off + (((uint32_t)(2 * j) ^ sw_xor) << 4), o0);
+                    st_shared_v4(stg + my_row_off + (((uint32_t)(2 * j + 1) ^ sw_xor) << 4), o1);
+                    if (j == jn - 1) {
+                      // unit complete: make the generic-proxy smem writes visible to the async proxy, one lane stores
+                      fence_proxy_async_smem();
+                      __syncwarp();
+                      if (lane == 0) {
+                        tma_store_4d(&tm_out, stg, col0 + cg0, t.w0 + g * kHaloTW, t.h0 + q * 4, t.img);
+                        bulk_commit();
+                      }
+                    }
+                  } else {
+                    *reinterpret_cast<uint4*>(obase + g * ostep + c) = o0;
+                    *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;
+                  }
+                }
               }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], lo_clamp);
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-              o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-              o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-              *reinterpret_cast<uint4*>(obase + g * ostep + c) = o0;
-              *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;
             }
           }
         }
@@ -412,12 +476,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar(acc));
+      if (warp == 2 && lane == 0) halo_trace(p, 401 + 2 * it);
     }
+    if (tma_out && lane == 0) bulk_wait_read<0>();     // smem must outlive the last store's read
   } else {
     // ------------------------------------------------------------ activation loaders (4 warps)
     const int lt = threadIdx.x - kHaloLoaderWarp0 * 32;
     pdl_wait();                              // activations are written by the previous kernel
     int s = 0; uint32_t ph = 0;
+    int nstage = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
       const HaloTile t = halo_decode<TG>(p, tile);
       const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
@@ -429,6 +496,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         const int pitch = (int)S.pitch;
         if (lane == 0) mbar_wait(aempty_bar(s), ph ^ 1u);
         __syncwarp();
+        if (lt == 0) halo_trace(p, 16 + 2 * nstage);
         const uint32_t dst0 = a_base + (uint32_t)s * A_STAGE_BYTES;
         if (!(p.dbg & 1)) {
 #pragma unroll 4
@@ -444,6 +512,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           }
         }
         cp_async_mbar_arrive_noinc(afull_bar(s));
+        if (lt == 0) halo_trace(p, 17 + 2 * nstage);
+        ++nstage;
         if (++s == p.a_stages) { s = 0; ph ^= 1u; }
       }
     }

@@ -148,7 +148,7 @@ struct ConvSpec {
 struct ConvLaunch {
   int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
   int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0;   // halo: template instantiation
-  CUtensorMap tm_act, tm_wgt;
+  CUtensorMap tm_act, tm_wgt, tm_out;
   ConvKArgs args;
   HaloKArgs hargs;
   unsigned grid = 0;
@@ -183,6 +183,8 @@ static FastDiv make_fastdiv(int d) {
   }
   return f;
 }
+
+static long long* g_halo_trace = nullptr;   // bench-only (uwm_debug_set_trace)
 
 static bool halo_enabled() {
   static int v = -1;
@@ -247,7 +249,11 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   //   issue  : the one MMA-issuing thread: ~60 instr per stage + ~12 per tap + ~3 per MMA, ~6 clk each (ncu)
   //   tensor : tg * nk * (kc/16) MMAs of max(32, bn/2) clk   (M=128: 32-clk floor below N=64)
   //   L2     : halo(tg)*cin*2 + (weights streamed ? bn*K*2 : 0) bytes per tile; ~64 B/clk per SM, 6300 B/clk chip
-  const size_t kBudget = 206u * 1024u;            // rings + resident weights (barriers/alignment slack on top)
+  // epilogue staging for TMA tensor stores (8 warps x 32 rows x 128 B): outputs with a multiple of 64 channels
+  static const bool ep_tma_enabled = []{ const char* e = getenv("UWM_EP_TMA"); return !(e && e[0] == '0'); }();
+  const bool ep_tma = ep_tma_enabled && !s.head && (s.cout_pad % 64 == 0);
+  const size_t stg_bytes = ep_tma ? (size_t)8 * 32 * 128 + 1024 : 0;
+  const size_t kBudget = 206u * 1024u - stg_bytes; // rings + resident weights (barriers/alignment slack on top)
   const int sms = num_sms();
   struct Cand { int bn, tg; bool resident; double cost; } best = {0, 0, false, 1e30};
   std::vector<int> bns;
@@ -339,6 +345,9 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.head = s.head; a.apply_sigmoid = s.apply_sigmoid;
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
   { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.trace = g_halo_trace;
+  a.ep_tma = ep_tma ? 1 : 0; a.ep_cols = ep_tma ? 64 : 16;
+  a.bias_smem = (s.cout_pad <= 1024) ? 1 : 0;
   { const char* e = getenv("UWM_VERBOSE");
     if (e && e[0] == '1')
       fprintf(stderr, "halo conv %dx%dx%d cin=%d(+%d%s) cout=%d %dx%d: bn=%d tg=%d kc=%d chunks=%d tiles=%d grid=%u a_stages=%d (%zu B) %s kpb=%d b_stages=%d\n",
@@ -346,7 +355,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
               a.a_stages, a_stage_bytes, best.resident ? "B resident" : "B streamed", a.kpb, a.b_stages); }
   L->grid = grid;
   const size_t b_total = best.resident ? resident_bytes : (size_t)a.b_stages * a.kpb * a.b_slice_bytes;
-  L->smem = 1024 + b_total + (size_t)a.a_stages * a_stage_bytes + 1024;
+  L->smem = 1024 + b_total + (size_t)a.a_stages * a_stage_bytes + stg_bytes + 1024 + (a.bias_smem ? (size_t)s.cout_pad * 4 : 0);
 
   const CUtensorMapSwizzle sw = (kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
                               : (kc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -361,6 +370,21 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(wgt) -> %d (k=%llu cout=%d)", (int)r, (unsigned long long)ktot, s.cout_pad);
+  if (ep_tma) {
+    // output view [n][h][w][cout] (pixel pitch out_pitch): boxes of 64 channels x 8 x 4 pixels, 128B-swizzled in smem
+    cuuint64_t odims[4] = {(cuuint64_t)s.cout, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
+    cuuint64_t ostr[3] = {(cuuint64_t)s.out_pitch * 2, (cuuint64_t)s.w * s.out_pitch * 2,
+                          (cuuint64_t)s.h * s.w * s.out_pitch * 2};
+    cuuint32_t obox[4] = {64, (cuuint32_t)kHaloTW, 4, 1};
+    cuuint32_t oest[4] = {1, 1, 1, 1};
+    r = enc(&L->tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s.out, odims, ostr, obox, oest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(out) -> %d (c=%d w=%d h=%d n=%d pitch=%lld)", (int)r, s.cout, s.w, s.h,
+                  s.n, s.out_pitch);
+  } else {
+    L->tm_out = L->tm_wgt;    // unused by the kernel
+  }
   return UWM_OK;
 }
 
@@ -493,9 +517,9 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
 #define UWM_HALO_CASE(KC, KH, KW, TG, RES)                                                                      \
   if (!L) {                                                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES>,                                        \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));                    \
   } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES) {           \
-    launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->hargs);     \
+    launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, L->hargs); \
     return UWM_OK;                                                                                              \
   }
   UWM_HALO_CASE(16, 3, 3, 1, true) UWM_HALO_CASE(16, 3, 3, 2, true) UWM_HALO_CASE(16, 3, 3, 4, true) UWM_HALO_CASE(16, 3, 3, 8, true)
@@ -1169,6 +1193,8 @@ extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int
 // ------------------------------------------------------------------------------------------
 // micro-benchmarks (sizing experiments; not part of the product path)
 // ------------------------------------------------------------------------------------------
+extern "C" int uwm_debug_set_trace(long long* d_trace) { g_halo_trace = d_trace; return UWM_OK; }
+
 extern "C" int uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int blocks, long long* d_cycles, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 1024 + (size_t)distinct_stages * (16384 + 32768);
