@@ -197,7 +197,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (s.stride != 1) return fail(UWM_EINVAL, "halo conv: stride %d unsupported", s.stride);
-  if (s.cin % 16 || s.cin2 % 16) return fail(UWM_EINVAL, "halo conv: cin=%d+%d must be multiples of 16", s.cin, s.cin2);
+  if (s.cin % 16 || s.cin2 % 16) return fail(UWM_EINVAL, "halo conv: cin=%d+%d: each must be a multiple of 16", s.cin, s.cin2);
   if (s.cout_pad % 16) return fail(UWM_EINVAL, "halo conv: cout_pad=%d must be a multiple of 16", s.cout_pad);
   if (s.ntaps < 1 || s.ntaps > kMaxTaps) return fail(UWM_EINVAL, "halo conv: %d taps unsupported", s.ntaps);
   if (s.h_out != s.h || s.w_out != s.w) return fail(UWM_EINVAL, "halo conv: needs 'same' padding (%dx%d -> %dx%d)", s.h, s.w, s.h_out, s.w_out);

@@ -256,7 +256,7 @@ class Unet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _run(self, x: torch.Tensor, want_logits: bool, threshold, sigmoid_threshold: bool,
-             force_sigmoid: bool = False):
+             force_sigmoid: bool = False, mask_out: Optional[torch.Tensor] = None):
         if not x.is_cuda:
             raise RuntimeError("unet_watermark_b200.Unet runs only on CUDA (sm_100a) tensors; there is no CPU "
                                "fallback. Move the model and the input to a B200 (`.to('cuda')`).")
@@ -278,7 +278,7 @@ class Unet(nn.Module):
             return eng.forward(x, want_logits=want_logits, threshold=threshold,
                                sigmoid_threshold=sigmoid_threshold,
                                apply_sigmoid=(self.activation_name == "sigmoid" or force_sigmoid),
-                               use_graph=self.use_cuda_graph)
+                               use_graph=self.use_cuda_graph, mask_out=mask_out)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -294,17 +294,21 @@ class Unet(nn.Module):
 
     @torch.no_grad()
     def predict_mask(self, x: torch.Tensor, threshold: float = 0.5, sigmoid: bool = True,
-                     return_logits: bool = False):
+                     return_logits: bool = False, out: Optional[torch.Tensor] = None):
         """Fused forward + threshold: uint8 ``[B,H,W]`` mask with values {0,255}.
 
         ``sigmoid=True``: ``sigmoid(logit) > threshold`` (reference src/scripts/watermark_filter.py:136-150,
         evaluated as ``logit > log(t/(1-t))``); ``sigmoid=False``: raw output ``> threshold``
         (reference src/predict.py:624-625).  ``x`` may be fp32 NCHW (normalised) or uint8 NHWC RGB
-        (normalisation fused on the GPU)."""
+        (normalisation fused on the GPU).  ``out``: optional caller-owned uint8 ``[B,H,W]`` CUDA buffer for the
+        mask; with stable input/output buffers every call replays one cached CUDA graph."""
         if self.activation_name == "sigmoid" and not sigmoid:
             # the model output already is a probability: compare it against thr  <=>  logit > logit(thr)
             sigmoid = True
-        logits, mask = self._run(x, return_logits, threshold, sigmoid)
+        if out is not None and (out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous()
+                                or tuple(out.shape) != (x.shape[0],) + tuple(x.shape[1:3] if x.dtype == torch.uint8 else x.shape[2:4])):
+            raise ValueError("out must be a contiguous CUDA uint8 tensor of shape [B,H,W]")
+        logits, mask = self._run(x, return_logits, threshold, sigmoid, mask_out=out)
         return (mask, logits) if return_logits else mask
 
     @torch.no_grad()
