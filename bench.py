@@ -150,6 +150,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     lib = _lib.load()
@@ -298,8 +300,8 @@ def run_ours(args):
                            "cuda_graph": True},
                 "tflops": value * eng.flops_per_image / 1e12,
                 "frac_of_bf16_peak": value * eng.flops_per_image / 1e12 / world / peaks["bf16_tflops"],
-                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": BATCH * SIZE * SIZE * 3,
-                        "d2h_bytes_per_step": BATCH * SIZE * SIZE, "ms_per_step": ms_e2e / args.steps,
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": world * BATCH * SIZE * SIZE * 3,
+                        "d2h_bytes_per_step": world * BATCH * SIZE * SIZE, "ms_per_step": ms_e2e / args.steps,
                         "api": "pinned host uint8 NHWC -> H2D -> Unet.predict_mask(x, 0.5, out=) -> D2H -> pinned host uint8 masks; "
                                "double-buffered over H2D / compute / D2H streams",
                         "mask_checksum": e2e_checksum},
