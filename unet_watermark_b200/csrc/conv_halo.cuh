@@ -155,9 +155,10 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
   return t;
 }
 
-template <int KC, int KH, int KW, int TG, bool RESIDENT>
+template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
+                 const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                  const __grid_constant__ HaloKArgs p) {
   constexpr int NT = KH * KW;
   constexpr int CPS = KC / 8;                               // 8-channel planes per stage
@@ -166,7 +167,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   constexpr int NPIX = halo_npix(TG, KH, KW);
   constexpr uint32_t PLANE_BYTES = halo_plane_bytes(TG, KH, KW);
   constexpr uint32_t PLANE_UNITS = PLANE_BYTES >> 4;
-  constexpr uint32_t A_STAGE_BYTES = CPS * PLANE_BYTES;
+  // A_TMA: the halo is one TMA box (KC channels x halo_w x halo_h pixels) in the swizzled pixel-major layout
+  // (row = pixel, KC*2 bytes); the tap / sub-tile shift is a whole number of rows.  TMA and the MMA unit both
+  // derive the swizzle XOR from the absolute shared-memory address, so a start address that is not aligned to
+  // the 8-row swizzle atom still reads what TMA wrote.
+  constexpr uint32_t ROWB = KC * 2;
+  constexpr uint32_t A_STAGE_BYTES = A_TMA ? ((uint32_t)NPIX * ROWB + 1023u) & ~1023u : CPS * PLANE_BYTES;
   constexpr int ITEMS = NPIX * CPS;                         // 16-byte pieces per stage
   constexpr uint32_t B_LAYOUT = (KC == 64) ? kLayoutSw128 : (KC == 32) ? kLayoutSw64 : kLayoutSw32;
 
@@ -202,13 +208,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   if (p.bias_smem)
     for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += kHaloThreads) s_bias[i] = __ldg(p.bias + i);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), A_TMA ? 1 : kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
     mbar_init(bres_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
     if (p.ep_tma) tma_prefetch_desc(&tm_out);
+    if (A_TMA) { tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); }
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(s_tmem_slot), p.tmem_cols);
@@ -257,8 +264,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     // ------------------------------------------------------------ MMA issuer (one elected thread)
     const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
     // A: no-swizzle K-major.  hi = SBO (halo row) | version;  lo = start>>4 | LBO (plane stride) << 16
-    constexpr uint32_t a_hi = (uint32_t)PW | (1u << 14);
-    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (PLANE_UNITS << 16);
+    constexpr uint32_t a_hi = A_TMA ? (((uint32_t)PW * ROWB) >> 4) | (1u << 14) | (B_LAYOUT << 29) : (uint32_t)PW | (1u << 14);
+    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | ((A_TMA ? 1u : PLANE_UNITS) << 16);
+    constexpr uint32_t a_px_units = A_TMA ? (ROWB >> 4) : 1u;      // 16-byte units per halo pixel step
+    constexpr uint32_t a_k_units = A_TMA ? 2u : 2u * PLANE_UNITS;   // 16-byte units per K=16 slice
     constexpr uint32_t a_stage_units = A_STAGE_BYTES >> 4;
     // B: swizzled K-major slices, rows of KC*2 bytes
     constexpr uint32_t b_hi = ((8u * KC * 2u) >> 4) | (1u << 14) | (B_LAYOUT << 29);
@@ -281,7 +290,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         for (int ch = 0; ch < p.chunks; ++ch) {
           mbar_wait_fast(afull_bar(sa), pha);
           if (ch == 0) halo_trace(p, 161 + 3 * it);
-          fence_proxy_async_smem();        // loaders wrote through the generic proxy (cp.async)
+          if (!A_TMA) fence_proxy_async_smem();        // loaders wrote through the generic proxy (cp.async)
           tc_fence_after();
           const uint32_t a_st = a_lo0 + (uint32_t)sa * a_stage_units;
           uint32_t b_lo = b_lo0 + (uint32_t)(ch * NT) * b_slice_units;   // resident: slice (ch, tap 0)
@@ -300,10 +309,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
                   if (tap == 0 && k == 0)
-                    umma_halo<false>(tmem_acc + g * bn, a_st + shift + 8u * g + 2u * k * PLANE_UNITS, a_hi,
+                    umma_halo<false>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
                                      b_lo + 2u * k, b_hi, idesc, (uint32_t)ch);
                   else
-                    umma_halo<true>(tmem_acc + g * bn, a_st + shift + 8u * g + 2u * k * PLANE_UNITS, a_hi,
+                    umma_halo<true>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
                                     b_lo + 2u * k, b_hi, idesc, 1u);
                 }
               }
@@ -485,6 +494,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     pdl_wait();                              // activations are written by the previous kernel
     int s = 0; uint32_t ph = 0;
     int nstage = 0;
+    if (A_TMA) {
+      // one thread, one TMA box per stage; out-of-image coordinates are zero-filled (= conv padding)
+      if (lt == 0) {
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
+          const HaloTile t = halo_decode<TG>(p, tile);
+          const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            mbar_wait(aempty_bar(s), ph ^ 1u);
+            halo_trace(p, 16 + 2 * nstage);
+            if (!(p.dbg & 1)) {
+              mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
+              if (ch < p.split_chunk)
+                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase, hbase, t.img);
+              else
+                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), (ch - p.split_chunk) * KC, wbase,
+                            hbase, t.img);
+            } else {
+              mbar_arrive(afull_bar(s));
+            }
+            halo_trace(p, 17 + 2 * nstage);
+            ++nstage;
+            if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
       const HaloTile t = halo_decode<TG>(p, tile);
       const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;

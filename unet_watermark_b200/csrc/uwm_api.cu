@@ -147,8 +147,8 @@ struct ConvSpec {
 
 struct ConvLaunch {
   int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
-  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0;   // halo: template instantiation
-  CUtensorMap tm_act, tm_wgt, tm_out;
+  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0;   // halo: template instantiation
+  CUtensorMap tm_act, tm_wgt, tm_out, tm_a0, tm_a1;
   ConvKArgs args;
   HaloKArgs hargs;
   unsigned grid = 0;
@@ -255,6 +255,13 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   const size_t stg_bytes = ep_tma ? (size_t)8 * 32 * 128 + 1024 : 0;
   const size_t kBudget = 206u * 1024u - stg_bytes; // rings + resident weights (barriers/alignment slack on top)
   const int sms = num_sms();
+  // activation halo by TMA (swizzled pixel-major stage) unless a source is upsampled on the fly
+  static const bool a_tma_enabled = []{ const char* e = getenv("UWM_A_TMA"); return !(e && e[0] == '0'); }();
+  const bool a_tma = a_tma_enabled && !s.up1;
+  auto a_stage_of = [&](int tg) -> size_t {
+    if (a_tma) return (((size_t)halo_npix(tg, kh, kw) * kc * 2) + 1023) & ~(size_t)1023;
+    return (size_t)cps * halo_plane_bytes(tg, kh, kw);
+  };
   struct Cand { int bn, tg; bool resident; double cost; } best = {0, 0, false, 1e30};
   std::vector<int> bns;
   if (s.cout_pad <= 64) bns.push_back(s.cout_pad);
@@ -269,7 +276,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       if (2 * tg * bn > 512) break;                               // two TMEM accumulator sets
       if (tg > 1 && tg > w8) break;                               // tile wider than the image
       if (force_tg && tg != force_tg && force_tg <= w8 && 2 * force_tg * bn <= 512) continue;
-      const size_t a_stage = (size_t)cps * halo_plane_bytes(tg, kh, kw);
+      const size_t a_stage = a_stage_of(tg);
       const size_t b_slice = ((size_t)bn * kc * 2 + 1023) & ~(size_t)1023;
       const int n_tiles = s.cout_pad / bn;
       const bool resident = (n_tiles == 1) && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
@@ -292,7 +299,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   }
   if (!best.bn) return fail(UWM_EINVAL, "halo conv: no tile fits shared memory (cin=%d cout=%d)", cin_total, s.cout_pad);
   const int bn = best.bn, tg = best.tg;
-  L->kh = kh; L->kw = kw; L->kc = kc; L->tg = tg; L->resident = best.resident ? 1 : 0;
+  L->kh = kh; L->kw = kw; L->kc = kc; L->tg = tg; L->resident = best.resident ? 1 : 0; L->a_tma = a_tma ? 1 : 0;
   a.tiles_w = (s.w + kHaloTW * tg - 1) / (kHaloTW * tg);
   a.tiles_h = (s.h + kHaloTH - 1) / kHaloTH;
   const int m_tiles = a.tiles_w * a.tiles_h * s.n;
@@ -300,7 +307,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.pw_magic = 65536u / (uint32_t)pw + 1u;
   for (int p = 0; p < npix; ++p)
     if ((int)(((uint32_t)p * a.pw_magic) >> 16) != p / pw) return fail(UWM_ESTATE, "halo conv: division magic failed for pw=%d", pw);
-  const size_t a_stage_bytes = (size_t)cps * halo_plane_bytes(tg, kh, kw);
+  const size_t a_stage_bytes = a_stage_of(tg);
   a.block_n = bn;
   a.n_tiles = s.cout_pad / bn;
   a.cout = s.cout;
@@ -384,6 +391,24 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
                   s.n, s.out_pitch);
   } else {
     L->tm_out = L->tm_wgt;    // unused by the kernel
+  }
+  L->tm_a0 = L->tm_wgt; L->tm_a1 = L->tm_wgt;
+  if (a_tma) {
+    for (int i = 0; i < 2; ++i) {
+      if (i == 1 && !s.x2) { L->tm_a1 = L->tm_a0; break; }
+      const void* base = i ? s.x2 : s.x;
+      const long long pitch = i ? s.x2_pitch : s.x_pitch;
+      const int csrc = i ? s.cin2 : s.cin;
+      cuuint64_t adims[4] = {(cuuint64_t)csrc, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
+      cuuint64_t astr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)s.w * pitch * 2, (cuuint64_t)s.h * s.w * pitch * 2};
+      cuuint32_t abox[4] = {(cuuint32_t)kc, (cuuint32_t)halo_pw(tg, kw), (cuuint32_t)(kHaloTH + kh - 1), 1};
+      cuuint32_t aest[4] = {1, 1, 1, 1};
+      r = enc(i ? &L->tm_a1 : &L->tm_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), adims, astr, abox,
+              aest, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS)
+        return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(act %d) -> %d (c=%d w=%d h=%d n=%d pitch=%lld box=%u,%u,%u)", i, (int)r,
+                    csrc, s.w, s.h, s.n, pitch, abox[0], abox[1], abox[2]);
+    }
   }
   return UWM_OK;
 }
@@ -514,14 +539,17 @@ static int build_conv_stream(const ConvSpec& s, ConvLaunch* L) {
 // Instantiation table of conv_halo_kernel<KC, KH, KW, TG, RESIDENT>.  L == nullptr: raise the dynamic
 // shared-memory limit of every instantiation (once); otherwise launch the one matching L.
 static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
-#define UWM_HALO_CASE(KC, KH, KW, TG, RES)                                                                      \
+#define UWM_HALO_CASE1(KC, KH, KW, TG, RES, AT)                                                                 \
   if (!L) {                                                                                                     \
-    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES>,                                        \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES, AT>,                                    \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));                    \
-  } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES) {           \
-    launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, L->hargs); \
+  } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES &&           \
+             (L->a_tma != 0) == AT) {                                                                           \
+    launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
+               L->tm_a0, L->tm_a1, L->hargs);                                                                   \
     return UWM_OK;                                                                                              \
   }
+#define UWM_HALO_CASE(KC, KH, KW, TG, RES) UWM_HALO_CASE1(KC, KH, KW, TG, RES, false) UWM_HALO_CASE1(KC, KH, KW, TG, RES, true)
   UWM_HALO_CASE(16, 3, 3, 1, true) UWM_HALO_CASE(16, 3, 3, 2, true) UWM_HALO_CASE(16, 3, 3, 4, true) UWM_HALO_CASE(16, 3, 3, 8, true)
   UWM_HALO_CASE(32, 3, 3, 1, true) UWM_HALO_CASE(32, 3, 3, 2, true) UWM_HALO_CASE(32, 3, 3, 4, true) UWM_HALO_CASE(32, 3, 3, 8, true)
   UWM_HALO_CASE(64, 3, 3, 1, true) UWM_HALO_CASE(64, 3, 3, 2, true) UWM_HALO_CASE(64, 3, 3, 4, true)
@@ -530,9 +558,10 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   UWM_HALO_CASE(64, 3, 3, 1, false) UWM_HALO_CASE(64, 3, 3, 2, false)
   UWM_HALO_CASE(16, 4, 4, 1, true) UWM_HALO_CASE(16, 4, 4, 2, true) UWM_HALO_CASE(16, 4, 4, 4, true) UWM_HALO_CASE(16, 4, 4, 8, true)
 #undef UWM_HALO_CASE
+#undef UWM_HALO_CASE1
   if (!L) return UWM_OK;
-  return fail(UWM_ESTATE, "halo conv: no kernel instantiated for kc=%d %dx%d tg=%d resident=%d", L->kc, L->kh, L->kw,
-              L->tg, L->resident);
+  return fail(UWM_ESTATE, "halo conv: no kernel instantiated for kc=%d %dx%d tg=%d resident=%d a_tma=%d", L->kc, L->kh,
+              L->kw, L->tg, L->resident, L->a_tma);
 }
 
 static int set_conv_attrs() {
