@@ -84,6 +84,7 @@ struct HaloKArgs {
   int kpb, b_stages;                        // streamed weights: kpb taps per stage (divides the tap count)
   uint32_t b_slice_bytes;                   // one (tap, chunk) slice, multiple of 1024
   uint32_t tmem_cols;
+  int nacc_log2;                            // log2 of the accumulator sets in TMEM (1 or 2)
   // epilogue
   const float* bias;
   const __nv_bfloat16* res;
@@ -193,12 +194,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxStages + s); };
   auto bempty_bar = [&](int s) { return bar_base + 8u * (3 * kHaloMaxStages + s); };
   auto accf_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + a); };
-  auto acce_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + 2 + a); };
-  const uint32_t bres_bar = bar_base + 8u * (4 * kHaloMaxStages + 4);
-  uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 6));
+  auto acce_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + 4 + a); };
+  const uint32_t bres_bar = bar_base + 8u * (4 * kHaloMaxStages + 8);
+  uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 10));
   // folded-BN bias of every output channel, staged once: the epilogue re-reads it per 16-column chunk, and the
   // trace showed that re-read missing L1 (an L2 round trip of 500-800 cycles in front of the first FADD)
-  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 8));
+  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 12));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,7 +211,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), A_TMA ? 1 : kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
+    for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
     mbar_init(bres_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
@@ -226,6 +227,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_slot;
   const int G = gridDim.x;
+  // accumulator sets in TMEM (2 or 4): the MMA -> epilogue -> MMA hand-back is a ~3000-cycle round trip even
+  // with nothing to do, so short tiles need more than two sets in flight
+  const int nacc_log2 = p.nacc_log2, nacc_mask = (1 << nacc_log2) - 1;
   if (threadIdx.x == 0) halo_trace(p, 1);
 
   if (warp == 0) {
@@ -282,9 +286,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       int sb = 0; uint32_t phb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
-        const int acc = it & 1;
+        const int acc = it & nacc_mask;
         const uint32_t tmem_acc = tmem_base + (uint32_t)acc * (TG * bn);
-        mbar_wait_fast(acce_bar(acc), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_wait_fast(acce_bar(acc), ((uint32_t)(it >> nacc_log2) & 1u) ^ 1u);
         tc_fence_after();
         halo_trace(p, 160 + 3 * it);
         for (int ch = 0; ch < p.chunks; ++ch) {
@@ -361,7 +365,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
-      const int acc = it & 1;
+      const int acc = it & nacc_mask;
       const HaloTile t = halo_decode<TG>(p, tile);
       const int oh = t.h0 + hi;
       const int ow0 = t.w0 + wi;
@@ -370,7 +374,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       const long long pix0 = ((long long)t.img * p.h + oh) * p.w + ow0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (TG * bn);
 
-      if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> 1) & 1u);
+      if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> nacc_log2) & 1u);
       __syncwarp();
       tc_fence_after();
       if (warp == 2 && lane == 0) halo_trace(p, 400 + 2 * it);

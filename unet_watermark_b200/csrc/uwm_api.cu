@@ -341,8 +341,10 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     a.a_stages = (int)std::max<size_t>(2, std::min<size_t>(kHaloMaxStages, (kBudget - a.b_stages * b_stage) / a_stage_bytes));
   }
   { const char* e = getenv("UWM_HALO_ASTAGES"); if (e && atoi(e) >= 2) a.a_stages = std::min(a.a_stages, atoi(e)); }
+  a.nacc_log2 = (4 * tg * bn <= 512) ? 2 : 1;
+  { const char* e = getenv("UWM_NACC"); if (e && atoi(e) == 2) a.nacc_log2 = 1; }
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)(tg * bn)) cols <<= 1;
+  while (cols < (uint32_t)((1 << a.nacc_log2) * tg * bn)) cols <<= 1;
   a.tmem_cols = cols;
   a.bias = s.bias;
   a.res = static_cast<const __nv_bfloat16*>(s.res);
