@@ -168,6 +168,9 @@ int    uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int b
  * events into d_trace[0..600) (tools/gpu_trace.py decodes them).  NULL switches tracing off. */
 int    uwm_debug_set_trace(long long* d_trace);
 
+/* Sizing micro-benchmark: cycles of one synchronisation primitive (tools/gpu_microbench3.py); d_out: 16 int64. */
+int    uwm_debug_prim_cost(int which, int iters, long long* d_out, void* stream);
+
 /* Sizing micro-benchmark: mbarrier ping-pong between two warps, cycles for `iters` round trips. */
 int    uwm_debug_handshake(int iters, int variant, int blocks, long long* d_cycles, void* stream);
 

@@ -65,6 +65,7 @@ SIGNATURES = {
                                     C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.c_int, _P]),
     "uwm_debug_set_trace": (C.c_int, [_P]),
+    "uwm_debug_prim_cost": (C.c_int, [C.c_int, C.c_int, _P, _P]),
     "uwm_debug_handshake": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
     "uwm_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
 }

@@ -106,3 +106,34 @@ __global__ void __launch_bounds__(64, 1) handshake_kernel(int iters, int variant
   }
 }
 }  // namespace uwm
+
+namespace uwm {
+// Cost of single synchronisation primitives: one warp executes `iters` repetitions, cycles per repetition.
+// which: 0 empty loop, 1 tcgen05.fence::before_thread_sync, 2 tcgen05.fence::after_thread_sync, 3 fence.proxy.async,
+// 4 mbarrier.arrive (lane 0) on a count-1 barrier, 5 __syncwarp, 6 try_wait on a completed phase (lane 0),
+// 7 lane-0 try_wait + __syncwarp, 8 tcgen05.commit to a barrier (lane 0), 9 clock64 + global store (lane 0)
+__global__ void __launch_bounds__(32, 1) prim_cost_kernel(int which, int iters, long long* out) {
+  __shared__ uint64_t bar[2];
+  const int lane = threadIdx.x;
+  if (lane == 0) { mbar_init(smem_u32(&bar[0]), 1); mbar_init(smem_u32(&bar[1]), 1); fence_mbar_init(); }
+  __syncwarp();
+  const uint32_t b0 = smem_u32(&bar[0]);
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    switch (which) {
+      case 1: tc_fence_before(); break;
+      case 2: tc_fence_after(); break;
+      case 3: asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); break;
+      case 4: if (lane == 0) mbar_arrive(b0); break;
+      case 5: __syncwarp(); break;
+      case 6: if (lane == 0) mbar_try_wait(b0, 1); break;
+      case 7: if (lane == 0) mbar_try_wait(b0, 1); __syncwarp(); break;
+      case 8: if (lane == 0) umma_commit(b0); break;
+      case 9: if (lane == 0) out[8 + (i & 7)] = clock64(); break;
+      default: asm volatile("" ::: "memory"); break;
+    }
+  }
+  long long t1 = clock64();
+  if (lane == 0) out[0] = t1 - t0;
+}
+}  // namespace uwm

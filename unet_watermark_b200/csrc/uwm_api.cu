@@ -1224,6 +1224,12 @@ extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int
 // ------------------------------------------------------------------------------------------
 // micro-benchmarks (sizing experiments; not part of the product path)
 // ------------------------------------------------------------------------------------------
+extern "C" int uwm_debug_prim_cost(int which, int iters, long long* d_out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  prim_cost_kernel<<<1, 32, 0, st>>>(which, iters, d_out);
+  return post_launch("prim_cost_kernel", st);
+}
+
 extern "C" int uwm_debug_set_trace(long long* d_trace) { g_halo_trace = d_trace; return UWM_OK; }
 
 extern "C" int uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int blocks, long long* d_cycles, void* stream) {
