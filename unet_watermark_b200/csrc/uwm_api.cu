@@ -231,7 +231,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   for (int t = 0; t < s.ntaps; ++t)
     if (s.dh[t] != dh_min + t / kw || s.dw[t] != dw_min + t % kw)
       return fail(UWM_EINVAL, "halo conv: taps must be in row-major order");
-  if (!((kh == 3 && kw == 3) || (kh == 4 && kw == 4 && kc == 16)))
+  if (!((kh == 3 && kw == 3) || (kh == 1 && kw == 1) || (kh == 4 && kw == 4 && kc == 16)))
     return fail(UWM_EINVAL, "halo conv: %dx%d filters with %d-channel chunks are not instantiated", kh, kw, kc);
   a.dh_min = dh_min; a.dw_min = dw_min;
   a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x);
@@ -282,6 +282,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const bool resident = (n_tiles == 1) && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
       if (!resident && (tg > 2 || 2 * b_slice + 2 * a_stage > kBudget)) break;   // streamed kernels: TG 1, 2
       if (kh == 4 && !resident) break;
+      if (kh == 1 && (tg > 4 || !a_tma)) break;                    // 1x1: TG 1, 2, 4, TMA-fed only
       const long long tiles = (long long)((s.w + kHaloTW * tg - 1) / (kHaloTW * tg)) * ((s.h + kHaloTH - 1) / kHaloTH) * s.n * n_tiles;
       const long long waves = (tiles + sms - 1) / sms;
       const double mmas = (double)tg * nk * (kc / 16);
@@ -423,6 +424,9 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   const bool fused = s.up1 || s.x2;
   const bool same = (s.stride == 1 && s.h_out == s.h && s.w_out == s.w);
   if (fused || (same && (s.ntaps == 9 || s.ntaps == 16) && halo_enabled())) return build_halo(s, L);
+  // 1x1 stride-1: TMA-fed halo kernel (no halo, but TMA stores and the two epilogue sets) when cin is a multiple of 64
+  static const bool pw_halo = []{ const char* e = getenv("UWM_PW_HALO"); return !(e && e[0] == '0'); }();
+  if (same && s.ntaps == 1 && s.cin % 64 == 0 && halo_enabled() && pw_halo) return build_halo(s, L);
   return build_conv_stream(s, L);
 }
 
@@ -559,6 +563,9 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   UWM_HALO_CASE(32, 3, 3, 1, false) UWM_HALO_CASE(32, 3, 3, 2, false)
   UWM_HALO_CASE(64, 3, 3, 1, false) UWM_HALO_CASE(64, 3, 3, 2, false)
   UWM_HALO_CASE(16, 4, 4, 1, true) UWM_HALO_CASE(16, 4, 4, 2, true) UWM_HALO_CASE(16, 4, 4, 4, true) UWM_HALO_CASE(16, 4, 4, 8, true)
+  // 1x1 stride-1 convs (resnet50 bottlenecks): plain GEMMs, TMA-fed, 64-channel chunks
+  UWM_HALO_CASE1(64, 1, 1, 1, true, true) UWM_HALO_CASE1(64, 1, 1, 2, true, true) UWM_HALO_CASE1(64, 1, 1, 4, true, true)
+  UWM_HALO_CASE1(64, 1, 1, 1, false, true) UWM_HALO_CASE1(64, 1, 1, 2, false, true)
 #undef UWM_HALO_CASE
 #undef UWM_HALO_CASE1
   if (!L) return UWM_OK;
