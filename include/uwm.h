@@ -42,6 +42,10 @@ extern "C" {
 
 /* weight packing kinds reported by uwm_model_layer_desc */
 #define UWM_PACK_TAPS     0   /* [cout_pad][kh*kw][cin] bf16, K index = (kh*kw_idx)*cin + c      */
+#define UWM_PACK_UP2X_SHUFFLE 2 /* conv3x3 over a nearest-2x upsampled input as a sub-pixel conv on the source grid:
+                                 [4*cout][3*3][cin] bf16, row (ph*2+pw)*cout + co, tap (a,b) holds the SUM (in fp32,
+                                 rounded once) of w[co,:,dy,dx] over the taps with floor((ph+dy-1)/2) == a-1 and
+                                 floor((pw+dx-1)/2) == b-1; bias = 4 copies (packing.pack_up2x_shuffle)          */
 #define UWM_PACK_STEM_S2D 1   /* 7x7/s2 stem as 4x4/s1 over the 2x2 space-to-depth input:
                                  [64][4*4][16] bf16, channel = (ph*2+pw)*3 + c, 12..15 zero      */
 
@@ -83,6 +87,16 @@ int uwm_conv2d_upcat_nhwc_bf16(const void* d_x, int n, int h, int w, int c_x, in
                                const void* d_wgt, const float* d_bias, int cout,
                                int kh, int kw, int pad, int relu,
                                void* d_y, int y_pitch, void* stream);
+
+/* conv3x3(pad 1) over F.interpolate(x, scale_factor=2, mode="nearest") WITHOUT a skip tensor (smp DecoderBlock 4 of the
+ * default Unet: interpolate + conv1), computed on the source grid: every output pixel (2i+ph, 2j+pw) sees only a 2x2
+ * neighbourhood of x, so the 9 taps collapse to 4 per parity.  One 3x3 conv x[n,h,w,cin] -> 4*cout channels with
+ * UWM_PACK_UP2X_SHUFFLE weights, whose epilogue scatters channel group (ph,pw) to pixel (2i+ph, 2j+pw) of
+ * y[n,2h,2w,cout] (pixel shuffle).  2.6x fewer tensor-pipe cycles than the N=cout conv at the upsampled resolution.
+ * cout multiple of 16, <= 64. */
+int uwm_conv2d_up2x_shuffle_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                      const void* d_wgt /*[4*cout][9*cin]*/, const float* d_bias /*[4*cout]*/,
+                                      int cout, int relu, void* d_y, int y_pitch, void* stream);
 
 /* Segmentation head: conv3x3(cin -> 1, bias) + optional sigmoid + threshold + uint8 mask.
  * Replaces smp SegmentationHead and `(mask > thr)*255`

@@ -60,3 +60,12 @@ UPCAT_CASES = [
     ("upcat_pitched",        2,  8,  8,  64,  64,  64, True,  True,  32, 64),
     ("upcat_persistent",     2, 128, 128, 32,  0,  16, True,  True,  0, 0),    # many tiles per CTA
 ]
+
+# Sub-pixel form of conv3x3(nearest_up2x(x)) without a skip — uwm_conv2d_up2x_shuffle_nhwc_bf16.
+# (name, n, h_lo, w_lo, cin, cout, relu)
+SHUFFLE_CASES = [
+    ("d4_up32_16_subpixel",   1, 32, 64, 32, 16, True),
+    ("subpixel_ragged",       2, 12, 20, 48, 32, False),     # 24x40 output; 4*32 = 128 GEMM columns
+    ("subpixel_64",           1, 16, 16, 64, 64, True),      # 4*64 = 256 GEMM columns (two N tiles possible)
+    ("subpixel_persistent",   2, 128, 128, 32, 16, True),
+]

@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.op_cases import CONV_CASES, UPCAT_CASES
+from tests.op_cases import CONV_CASES, SHUFFLE_CASES, UPCAT_CASES
 from unet_watermark_b200 import _lib, ops, packing
 
 pytestmark = pytest.mark.gpu
@@ -72,6 +72,31 @@ def test_upcat_conv_matches_fp32_reference(case, cuda_device):
     ref = ref.permute(0, 2, 3, 1)
     err = (out.float() - ref).abs()
     assert bool((err <= 1e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+
+
+@pytest.mark.parametrize("case", SHUFFLE_CASES, ids=[c[0] for c in SHUFFLE_CASES])
+def test_subpixel_conv_matches_fp32_reference(case, cuda_device):
+    """conv3x3(interpolate(x, 2, nearest)) computed on the source grid (pre-summed taps + pixel shuffle) vs the two
+    torch ops.  The pre-summed weights are rounded once to bf16, so the tolerance is the per-op one plus one extra
+    weight rounding: |err| <= 1.5e-2 * max(1, |ref|) against the reference on the ORIGINAL bf16-rounded weights."""
+    name, n, h, w, cin, cout, relu = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    ws = packing.pack_up2x_shuffle(wt)
+    before = _lib.load().uwm_kernel_launch_count()
+    out = ops.conv2d_up2x_shuffle(x, ws, bias.repeat(4).contiguous(), relu=relu)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    assert out.shape == (n, 2 * h, 2 * w, cout)
+    xi = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(xi, wt.to(torch.bfloat16).float(), bias, padding=1)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1.5e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
 
 
 def test_conv_rejects_bad_arguments(cuda_device):

@@ -18,6 +18,7 @@ IN_F32_NCHW = 0
 IN_U8_NHWC = 1
 PACK_TAPS = 0
 PACK_STEM_S2D = 1
+PACK_UP2X_SHUFFLE = 2
 
 
 class LayerDesc(C.Structure):
@@ -45,6 +46,8 @@ SIGNATURES = {
     "uwm_conv2d_upcat_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int,
                                              C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                              C.c_int, _P]),
+    "uwm_conv2d_up2x_shuffle_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
+                                                    C.c_int, _P, C.c_int, _P]),
     "uwm_head_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,
                                      _P, C.c_float, _P]),
     "uwm_maxpool3x3s2_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),

@@ -96,6 +96,8 @@ struct HaloKArgs {
   uint8_t* mask;
   float thr_logit;
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
+  int shuffle;                              // > 0: sub-pixel mode, real cout; GEMM column n = parity*shuffle + co is stored to
+                                            // pixel (2h + parity/2, 2w + parity%2), channel co of the 2x larger output (pixel shuffle)
   int bias_smem;                            // bias of all n_tiles*block_n channels staged in smem (<= 1024 channels)
   long long* trace;                         // bench-only: CTA 0 writes clock64() stamps of its pipeline events (tools/gpu_trace.py)
   int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
@@ -476,6 +478,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                         bulk_commit();
                       }
                     }
+                  } else if (p.shuffle) {
+                    const int par = (col0 + c) / p.shuffle, co = col0 + c - par * p.shuffle;   // chunk -> (parity, channel)
+                    const long long hp = ((long long)(t.img * 2 * p.h + 2 * oh + (par >> 1)) * (2 * p.w) +
+                                          2 * (ow0 + g * kHaloTW) + (par & 1));
+                    __nv_bfloat16* dst = p.out + hp * p.out_pitch + co;
+                    *reinterpret_cast<uint4*>(dst) = o0;
+                    *reinterpret_cast<uint4*>(dst + 8) = o1;
                   } else {
                     *reinterpret_cast<uint4*>(obase + g * ostep + c) = o0;
                     *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;

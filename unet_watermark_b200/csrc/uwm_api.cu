@@ -139,6 +139,7 @@ struct ConvSpec {
   int relu = 0;
   void* out = nullptr;
   long long out_pitch = 0;
+  int shuffle = 0;                // sub-pixel conv: real cout; `cout`/`cout_pad` are then 4x that (one group per output parity)
   int head = 0, apply_sigmoid = 0;
   float* logits = nullptr;
   uint8_t* mask = nullptr;
@@ -251,7 +252,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   //   L2     : halo(tg)*cin*2 + (weights streamed ? bn*K*2 : 0) bytes per tile; ~64 B/clk per SM, 6300 B/clk chip
   // epilogue staging for TMA tensor stores (8 warps x 32 rows x 128 B): outputs with a multiple of 64 channels
   static const bool ep_tma_enabled = []{ const char* e = getenv("UWM_EP_TMA"); return !(e && e[0] == '0'); }();
-  const bool ep_tma = ep_tma_enabled && !s.head && (s.cout_pad % 64 == 0);
+  const bool ep_tma = ep_tma_enabled && !s.head && !s.shuffle && (s.cout_pad % 64 == 0);
   const size_t stg_bytes = ep_tma ? (size_t)8 * 32 * 128 + 1024 : 0;
   const size_t kBudget = 206u * 1024u - stg_bytes; // rings + resident weights (barriers/alignment slack on top)
   const int sms = num_sms();
@@ -356,6 +357,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
   { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.trace = g_halo_trace;
+  a.shuffle = s.shuffle;
   a.ep_tma = ep_tma ? 1 : 0; a.ep_cols = ep_tma ? 64 : 16;
   a.bias_smem = (s.cout_pad <= 1024) ? 1 : 0;
   { const char* e = getenv("UWM_VERBOSE");
@@ -659,6 +661,23 @@ extern "C" int uwm_conv2d_upcat_nhwc_bf16(const void* d_x, int n, int h, int w, 
   return launch_conv(L, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int uwm_conv2d_up2x_shuffle_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                                 const void* d_wgt, const float* d_bias, int cout, int relu, void* d_y,
+                                                 int y_pitch, void* stream) {
+  if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_up2x_shuffle: null pointer");
+  if (cout % 16 || 4 * cout > 256) return fail(UWM_EINVAL, "conv2d_up2x_shuffle: cout=%d must be a multiple of 16, <= 64", cout);
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = cin; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = 4 * cout; s.cout_pad = 4 * cout; s.shuffle = cout;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 1; s.h_out = h; s.w_out = w;
+  s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_halo(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int uwm_head_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
                                   const void* d_wgt, const float* d_bias, float* d_logits,
                                   int apply_sigmoid, uint8_t* d_mask, float thr_logit, void* stream) {
@@ -745,6 +764,7 @@ struct Op {
 struct Layer {
   uwm_layer_desc d;
   bool stem = false;
+  bool shuffle = false;    // decoder conv1 without a skip: 3x3 conv on the upsampled input as a sub-pixel conv
   void* d_w = nullptr;
   float* d_b = nullptr;
   bool set = false;
@@ -804,7 +824,8 @@ struct uwm_model {
 };
 
 static int add_layer(uwm_model* m, const std::string& conv_key, const std::string& bn_key, int cin,
-                     int cout, int k, int stride, int pad, int relu, int has_res, bool stem = false) {
+                     int cout, int k, int stride, int pad, int relu, int has_res, bool stem = false,
+                     bool shuffle = false) {
   Layer L;
   memset(&L.d, 0, sizeof(L.d));
   snprintf(L.d.conv_key, sizeof(L.d.conv_key), "%s", conv_key.c_str());
@@ -816,6 +837,13 @@ static int add_layer(uwm_model* m, const std::string& conv_key, const std::strin
   if (stem) {
     L.d.pack = UWM_PACK_STEM_S2D;
     L.d.w_elems = (int64_t)L.d.cout_pad * 16 * 16;
+  } else if (shuffle) {
+    // conv3x3 over a nearest-2x upsampled input == 3x3 conv on the SOURCE grid producing 4*cout channels (one group
+    // per output parity, weights pre-summed over the taps that hit the same source pixel) + pixel shuffle
+    L.shuffle = true;
+    L.d.pack = UWM_PACK_UP2X_SHUFFLE;
+    L.d.cout_pad = 4 * cout;                       // GEMM N; cout must be a multiple of 16 (checked at create)
+    L.d.w_elems = (int64_t)L.d.cout_pad * 9 * cin;
   } else {
     L.d.pack = UWM_PACK_TAPS;
     L.d.w_elems = (int64_t)L.d.cout_pad * k * k * cin;
@@ -851,6 +879,12 @@ static std::string fmt(const char* f, ...) {
   char b[160];
   va_list ap; va_start(ap, f); vsnprintf(b, sizeof(b), f, ap); va_end(ap);
   return b;
+}
+
+static bool subpixel_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UWM_SUBPIXEL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 static int build_plan(uwm_model* m) {
@@ -929,7 +963,8 @@ static int build_plan(uwm_model* m) {
     const int bh = H >> (4 - i), bw = W >> (4 - i);
     const std::string pre = fmt("decoder.blocks.%d", i);
     TRef t1 = m->dense(bh, bw, dec[i]);
-    int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0);
+    const bool subpixel = (cs[i] == 0) && subpixel_enabled() && 4 * dec[i] <= 256;
+    int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0, false, subpixel);
     add_conv(m, l1, x, t1, nullptr, false, /*up=*/true, cs[i] ? &skip[i] : nullptr);
     TRef t2 = m->dense(bh, bw, dec[i]);
     int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0);
@@ -1068,7 +1103,8 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
           s.h_out = op.in.h; s.w_out = op.in.w;
         } else {
           s.cin = op.in.c; s.stride = ly.d.stride;
-          if (op.up) { s.up1 = 1; s.h = op.in.h * 2; s.w = op.in.w * 2; }
+          if (ly.shuffle) { s.shuffle = ly.d.cout; s.cout = ly.d.cout_pad; }   // runs on the source grid, N = 4*cout
+          else if (op.up) { s.up1 = 1; s.h = op.in.h * 2; s.w = op.in.w * 2; }
           if (op.has_in2) { s.x2 = m->ptr(op.in2); s.cin2 = op.in2.c; s.x2_pitch = op.in2.pitch; }
           if (s.cin + s.cin2 != ly.d.cin)
             return fail(UWM_ESTATE, "plan bug: %s reads %d+%d channels, layer has %d", ly.d.conv_key, s.cin, s.cin2, ly.d.cin);
@@ -1080,8 +1116,10 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
         if (op.type == OP_HEAD) {
           s.head = 1; s.apply_sigmoid = apply_sigmoid; s.logits = d_logits; s.mask = d_mask; s.thr_logit = thr_logit;
         } else {
-          if (s.h_out != op.out.h || s.w_out != op.out.w)
-            return fail(UWM_ESTATE, "plan bug: %s output %dx%d != planned %dx%d", ly.d.conv_key, s.h_out, s.w_out, op.out.h, op.out.w);
+          const int up_out = ly.shuffle ? 2 : 1;       // the sub-pixel conv writes a 2x larger tensor
+          if (s.h_out * up_out != op.out.h || s.w_out * up_out != op.out.w)
+            return fail(UWM_ESTATE, "plan bug: %s output %dx%d != planned %dx%d", ly.d.conv_key, s.h_out * up_out,
+                        s.w_out * up_out, op.out.h, op.out.w);
           s.out = m->ptr(op.out); s.out_pitch = op.out.pitch;
           if (op.has_res) { s.res = m->ptr(op.res); s.res_pitch = op.res.pitch; }
         }

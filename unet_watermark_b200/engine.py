@@ -75,9 +75,13 @@ class Engine:
                 b = state[ck + ".bias"].detach().float().cpu()
             if d.pack == _lib.PACK_STEM_S2D:
                 wp = packing.pack_stem_s2d(w, d.cout_pad)
+                bp = packing.pad_bias(b, d.cout_pad)
+            elif d.pack == _lib.PACK_UP2X_SHUFFLE:
+                wp = packing.pack_up2x_shuffle(w)              # [4*cout, 9*cin]: one output group per parity
+                bp = b.detach().float().repeat(4).contiguous()
             else:
                 wp = packing.pack_taps(w, d.cout_pad)
-            bp = packing.pad_bias(b, d.cout_pad)
+                bp = packing.pad_bias(b, d.cout_pad)
             assert wp.numel() == d.w_elems and bp.numel() == d.b_elems, (ck, wp.shape, d.w_elems)
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.uwm_model_set_layer(self.handle, i, wp.data_ptr(), wp.numel(), bp.data_ptr(),

@@ -75,6 +75,22 @@ def conv2d_upcat(x: torch.Tensor, skip: Optional[torch.Tensor], w_packed: torch.
     return out
 
 
+def conv2d_up2x_shuffle(x: torch.Tensor, w_shuffle: torch.Tensor, bias4: torch.Tensor, relu: bool = True,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv3x3(nearest_up2x(x)) (+bias)(+ReLU) as a sub-pixel conv on the source grid.
+    w_shuffle: packing.pack_up2x_shuffle(w) = [4*Cout, 9*Cin] bf16; bias4: bias repeated 4x (fp32)."""
+    _require_cuda(x, w_shuffle, bias4, out)
+    lib = _lib.load()
+    n, h, w, cin = x.shape
+    cout = w_shuffle.shape[0] // 4
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_up2x_shuffle_nhwc_bf16(x.data_ptr(), n, h, w, cin, _pitch(x), w_shuffle.data_ptr(),
+                                               bias4.data_ptr(), cout, int(relu), out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_up2x_shuffle_nhwc_bf16")
+    return out
+
+
 def head(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, threshold: Optional[float] = 0.5,
          thr_on_logits: bool = False, want_logits: bool = True, apply_sigmoid: bool = False):
     """conv3x3(Cin->1)+bias -> (fp32 logits [N,H,W] or None, uint8 mask [N,H,W] or None)."""

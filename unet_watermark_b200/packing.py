@@ -48,6 +48,27 @@ def pack_stem_s2d(w: torch.Tensor, cout_pad: int | None = None) -> torch.Tensor:
     return out.reshape(cout_pad, 256).to(torch.bfloat16).contiguous()
 
 
+def pack_up2x_shuffle(w: torch.Tensor) -> torch.Tensor:
+    """3x3 conv applied to a nearest-2x upsampled input, as a 3x3 conv on the source grid with 4*Cout outputs.
+
+    Output pixel (2i+ph, 2j+pw) reads upsampled pixels (2i+ph+dy, 2j+pw+dx), dy,dx in {-1,0,1}, i.e. source pixels
+    (i + floor((ph+dy)/2), j + floor((pw+dx)/2)): taps that land on the same source pixel are summed (fp32) and the
+    sum is rounded once to bf16.  Returns bf16 [4*Cout, 9*Cin]; row (ph*2+pw)*Cout + co, K index (a*3+b)*Cin + c for
+    source offset (a-1, b-1).  The kernel's epilogue scatters group (ph,pw) to pixel (2i+ph, 2j+pw)."""
+    cout, cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3), "sub-pixel packing expects a 3x3 kernel"
+    wf = w.detach().float()
+    out = torch.zeros(2, 2, cout, 3, 3, cin, dtype=torch.float32, device=w.device)
+    for ph in range(2):
+        for pw in range(2):
+            for dy in (-1, 0, 1):
+                a = (ph + dy) // 2          # python floor division: -1 // 2 == -1
+                for dx in (-1, 0, 1):
+                    b = (pw + dx) // 2
+                    out[ph, pw, :, a + 1, b + 1, :] += wf[:, :, dy + 1, dx + 1]
+    return out.reshape(4 * cout, 9 * cin).to(torch.bfloat16).contiguous()
+
+
 def pad_bias(b: torch.Tensor, cout_pad: int) -> torch.Tensor:
     out = torch.zeros(cout_pad, dtype=torch.float32, device=b.device)
     out[: b.numel()] = b.detach().float()
