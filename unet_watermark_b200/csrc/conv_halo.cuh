@@ -35,6 +35,8 @@
 //               is latency-bound (one TMEM load -> math -> store chain at a time), so every quarter gets two
 //               warps that split the sub-tiles (or the 16-column chunks when TG == 1) of each tile
 #pragma once
+#include <type_traits>
+
 #include "conv_tc.cuh"
 
 namespace uwm {
@@ -98,7 +100,6 @@ struct HaloKArgs {
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
   int shuffle;                              // > 0: sub-pixel mode, real cout; GEMM column n = parity*shuffle + co is stored to
                                             // pixel (2h + parity/2, 2w + parity%2), channel co of the 2x larger output (pixel shuffle)
-  int bias_smem;                            // bias of all n_tiles*block_n channels staged in smem (<= 1024 channels)
   long long* trace;                         // bench-only: CTA 0 writes clock64() stamps of its pipeline events (tools/gpu_trace.py)
   int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
 };
@@ -208,8 +209,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) halo_trace(p, 0);
-  if (p.bias_smem)
-    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += kHaloThreads) s_bias[i] = __ldg(p.bias + i);
+  for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += kHaloThreads) s_bias[i] = __ldg(p.bias + i);
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), A_TMA ? 1 : kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
@@ -401,99 +401,101 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           }
         }
       } else {
-        __nv_bfloat16* obase = p.out + pix0 * p.out_pitch + col0;
-        const __nv_bfloat16* rbase = p.res ? p.res + pix0 * p.res_pitch + col0 : nullptr;
-        const long long ostep = (long long)kHaloTW * p.out_pitch, rstep = (long long)kHaloTW * p.res_pitch;
-        const float4* brow = reinterpret_cast<const float4*>(p.bias + col0);
+        // Items of this warp: 16-column chunk j of column group cg0 (64 columns with TMA stores, else 16) of
+        // sub-tile g.  The TMEM load of the next item and its residual are in flight while the current one is
+        // biased / ReLU'd / packed.  The item body is instantiated per output mode (generic lambda with
+        // compile-time flags): a warp runs ~4-10 cycles per instruction here, so the per-item branches of a
+        // run-time-configured loop cost as much as the arithmetic.
         const int ncols = min(p.block_n, p.cout - col0);
-        // Items: 16-column chunk j of column group cg (ep_cols = 16 or 64 columns) of sub-tile g.  The TMEM load
-        // of the next item and its residual are in flight while the current one is biased / ReLU'd / packed.
-        // ep_tma: the packed rows go to this warp's swizzled smem staging buffer and one lane issues a TMA tensor
-        // store per (sub-tile, 64-column group); otherwise each lane stores its pixel's 32 bytes directly.
-        const int log2_jn = (p.ep_cols == 64) ? 2 : 0;                    // chunks per column group: 4 or 1
-        const int jn = 1 << log2_jn;
-        const int NIT = GN << log2_jn;                                    // items per column group for this warp
-        for (int cg0 = c_first * jn; cg0 < ncols; cg0 += c_step * jn) {  // first column of the group
-          uint32_t v[2][16];
-          uint4 r0[2], r1[2];
-          auto item_load = [&](int n, int b) {
-            const int g = GSTEP * (n >> log2_jn) + g_first, c = cg0 + ((n & (jn - 1)) << 4);
-            tmem_ld_x16(taddr0 + (uint32_t)g * bn + c, v[b]);
-            r0[b] = make_uint4(0, 0, 0, 0); r1[b] = make_uint4(0, 0, 0, 0);
-            if (rbase && row_ok && (ow0 + g * kHaloTW < p.w)) {
-              r0[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
-              r1[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
-            }
-          };
-          item_load(0, 0);
-          for (int n0 = 0; n0 < NIT; n0 += 2) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int n = n0 + u;
-              if (n < NIT) {
-                const int j = n & (jn - 1);
-                const int g = GSTEP * (n >> log2_jn) + g_first, c = cg0 + (j << 4);
-                const bool valid = row_ok && (ow0 + g * kHaloTW < p.w);
-                float4 b0, b1, b2, b3;
-                if (p.bias_smem) {
-                  const float4* sb = reinterpret_cast<const float4*>(s_bias + col0 + c);
-                  b0 = sb[0]; b1 = sb[1]; b2 = sb[2]; b3 = sb[3];
-                } else {
-                  b0 = __ldg(brow + (c >> 2)); b1 = __ldg(brow + (c >> 2) + 1);
-                  b2 = __ldg(brow + (c >> 2) + 2); b3 = __ldg(brow + (c >> 2) + 3);
+        const uint32_t bsm = smem_u32(s_bias + col0);                     // folded-BN bias, staged in smem
+        auto run_items = [&](auto tma_c, auto res_c, auto shuf_c) {
+          constexpr bool TMA = decltype(tma_c)::value, RES = decltype(res_c)::value, SHUF = decltype(shuf_c)::value;
+          constexpr int LOG2_JN = TMA ? 2 : 0, JN = 1 << LOG2_JN;           // chunks per column group
+          constexpr int NIT = GN << LOG2_JN;                                // items per column group for this warp
+          __nv_bfloat16* obase = p.out + pix0 * p.out_pitch + col0;
+          const __nv_bfloat16* rbase = RES ? p.res + pix0 * p.res_pitch + col0 : nullptr;
+          const long long ostep = (long long)kHaloTW * p.out_pitch, rstep = (long long)kHaloTW * p.res_pitch;
+          for (int cg0 = c_first * JN; cg0 < ncols; cg0 += c_step * JN) {  // first column of the group
+            uint32_t v[2][16];
+            uint4 r0[2], r1[2];
+            auto item_load = [&](int n, int b) {
+              const int g = GSTEP * (n >> LOG2_JN) + g_first, c = cg0 + ((n & (JN - 1)) << 4);
+              tmem_ld_x16(taddr0 + (uint32_t)g * bn + c, v[b]);
+              if (RES) {
+                r0[b] = make_uint4(0, 0, 0, 0); r1[b] = make_uint4(0, 0, 0, 0);
+                if (row_ok && (ow0 + g * kHaloTW < p.w)) {
+                  r0[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
+                  r1[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
                 }
-                const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
-                                      b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
-                tmem_ld_wait();
-                if (n + 1 < NIT) item_load(n + 1, (u + 1) & 1);
-                if (valid || tma_out) {
-                  float f[16];
+              }
+            };
+            item_load(0, 0);
 #pragma unroll
-                  for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[u][k]) + bb[k];
-                  if (rbase) {
-                    const uint32_t rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+            for (int n = 0; n < NIT; ++n) {
+              const int u = n & 1;
+              const int j = n & (JN - 1);
+              const int g = GSTEP * (n >> LOG2_JN) + g_first, c = cg0 + (j << 4);
+              const bool valid = row_ok && (ow0 + g * kHaloTW < p.w);
+              const uint4 b0 = ld_shared_v4(bsm + c * 4), b1 = ld_shared_v4(bsm + c * 4 + 16);
+              const uint4 b2 = ld_shared_v4(bsm + c * 4 + 32), b3 = ld_shared_v4(bsm + c * 4 + 48);
+              const float bb[16] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                                    __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w),
+                                    __uint_as_float(b2.x), __uint_as_float(b2.y), __uint_as_float(b2.z), __uint_as_float(b2.w),
+                                    __uint_as_float(b3.x), __uint_as_float(b3.y), __uint_as_float(b3.z), __uint_as_float(b3.w)};
+              tmem_ld_wait();
+              if (n + 1 < NIT) item_load(n + 1, (n + 1) & 1);
+              if (valid || TMA) {
+                float f[16];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(rr[k]); f[2 * k + 1] += bf16_hi(rr[k]); }
+                for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[u][k]) + bb[k];
+                if (RES) {
+                  const uint32_t rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(rr[k]); f[2 * k + 1] += bf16_hi(rr[k]); }
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], lo_clamp);
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                if (TMA) {
+                  if (j == 0) {          // the previous store of this warp must have read the buffer out
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
                   }
-#pragma unroll
-                  for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], lo_clamp);
-                  uint4 o0, o1;
-                  o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                  o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                  o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                  o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                  if (tma_out) {
-                    if (j == 0) {          // the previous store of this warp must have read the buffer out
-                      if (lane == 0) bulk_wait_read<0>();
-                      __syncwarp();
+                  st_shared_v4(stg + my_row_off + (((uint32_t)(2 * j) ^ sw_xor) << 4), o0);
+                  st_shared_v4(stg + my_row_off + (((uint32_t)(2 * j + 1) ^ sw_xor) << 4), o1);
+                  if (j == JN - 1) {
+                    // unit complete: make the generic-proxy smem writes visible to the async proxy, one lane stores
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                      tma_store_4d(&tm_out, stg, col0 + cg0, t.w0 + g * kHaloTW, t.h0 + q * 4, t.img);
+                      bulk_commit();
                     }
-                    st_shared_v4(stg + my_row_off + (((uint32_t)(2 * j) ^ sw_xor) << 4), o0);
-                    st_shared_v4(stg + my_row_off + (((uint32_t)(2 * j + 1) ^ sw_xor) << 4), o1);
-                    if (j == jn - 1) {
-                      // unit complete: make the generic-proxy smem writes visible to the async proxy, one lane stores
-                      fence_proxy_async_smem();
-                      __syncwarp();
-                      if (lane == 0) {
-                        tma_store_4d(&tm_out, stg, col0 + cg0, t.w0 + g * kHaloTW, t.h0 + q * 4, t.img);
-                        bulk_commit();
-                      }
-                    }
-                  } else if (p.shuffle) {
-                    const int par = (col0 + c) / p.shuffle, co = col0 + c - par * p.shuffle;   // chunk -> (parity, channel)
-                    const long long hp = ((long long)(t.img * 2 * p.h + 2 * oh + (par >> 1)) * (2 * p.w) +
-                                          2 * (ow0 + g * kHaloTW) + (par & 1));
-                    __nv_bfloat16* dst = p.out + hp * p.out_pitch + co;
-                    *reinterpret_cast<uint4*>(dst) = o0;
-                    *reinterpret_cast<uint4*>(dst + 8) = o1;
-                  } else {
-                    *reinterpret_cast<uint4*>(obase + g * ostep + c) = o0;
-                    *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;
                   }
+                } else if (SHUF) {
+                  const int par = (col0 + c) / p.shuffle, co = col0 + c - par * p.shuffle;   // chunk -> (parity, channel)
+                  const long long hp = ((long long)(t.img * 2 * p.h + 2 * oh + (par >> 1)) * (2 * p.w) +
+                                        2 * (ow0 + g * kHaloTW) + (par & 1));
+                  __nv_bfloat16* dst = p.out + hp * p.out_pitch + co;
+                  *reinterpret_cast<uint4*>(dst) = o0;
+                  *reinterpret_cast<uint4*>(dst + 8) = o1;
+                } else {
+                  *reinterpret_cast<uint4*>(obase + g * ostep + c) = o0;
+                  *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;
                 }
               }
             }
           }
-        }
+        };
+        using T_ = std::true_type; using F_ = std::false_type;
+        if (tma_out) { if (p.res) run_items(T_{}, T_{}, F_{}); else run_items(T_{}, F_{}, F_{}); }
+        else if (p.shuffle) run_items(F_{}, F_{}, T_{});
+        else if (p.res) run_items(F_{}, T_{}, F_{});
+        else run_items(F_{}, F_{}, F_{});
       }
       tc_fence_before();
       __syncwarp();

@@ -200,6 +200,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   if (s.stride != 1) return fail(UWM_EINVAL, "halo conv: stride %d unsupported", s.stride);
   if (s.cin % 16 || s.cin2 % 16) return fail(UWM_EINVAL, "halo conv: cin=%d+%d: each must be a multiple of 16", s.cin, s.cin2);
   if (s.cout_pad % 16) return fail(UWM_EINVAL, "halo conv: cout_pad=%d must be a multiple of 16", s.cout_pad);
+  if (s.cout_pad > 2048) return fail(UWM_EINVAL, "halo conv: cout=%d > 2048 (bias staging)", s.cout_pad);
   if (s.ntaps < 1 || s.ntaps > kMaxTaps) return fail(UWM_EINVAL, "halo conv: %d taps unsupported", s.ntaps);
   if (s.h_out != s.h || s.w_out != s.w) return fail(UWM_EINVAL, "halo conv: needs 'same' padding (%dx%d -> %dx%d)", s.h, s.w, s.h_out, s.w_out);
   if (s.up1 && ((s.h | s.w) & 1)) return fail(UWM_EINVAL, "halo conv: upsampled size %dx%d must be even", s.h, s.w);
@@ -357,9 +358,9 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
   { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.trace = g_halo_trace;
+  { const char* e = getenv("UWM_TRACE_KH"); if (e && atoi(e) != kh) a.trace = nullptr; }   // bench-only: trace one filter shape
   a.shuffle = s.shuffle;
   a.ep_tma = ep_tma ? 1 : 0; a.ep_cols = ep_tma ? 64 : 16;
-  a.bias_smem = (s.cout_pad <= 1024) ? 1 : 0;
   { const char* e = getenv("UWM_VERBOSE");
     if (e && e[0] == '1')
       fprintf(stderr, "halo conv %dx%dx%d cin=%d(+%d%s) cout=%d %dx%d: bn=%d tg=%d kc=%d chunks=%d tiles=%d grid=%u a_stages=%d (%zu B) %s kpb=%d b_stages=%d\n",
@@ -367,7 +368,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
               a.a_stages, a_stage_bytes, best.resident ? "B resident" : "B streamed", a.kpb, a.b_stages); }
   L->grid = grid;
   const size_t b_total = best.resident ? resident_bytes : (size_t)a.b_stages * a.kpb * a.b_slice_bytes;
-  L->smem = 1024 + b_total + (size_t)a.a_stages * a_stage_bytes + stg_bytes + 1024 + (a.bias_smem ? (size_t)s.cout_pad * 4 : 0);
+  L->smem = 1024 + b_total + (size_t)a.a_stages * a_stage_bytes + stg_bytes + 1024 + (size_t)s.cout_pad * 4;
 
   const CUtensorMapSwizzle sw = (kc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
                               : (kc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -550,7 +551,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
 #define UWM_HALO_CASE1(KC, KH, KW, TG, RES, AT)                                                                 \
   if (!L) {                                                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES, AT>,                                    \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                    \
   } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES &&           \
              (L->a_tma != 0) == AT) {                                                                           \
     launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
