@@ -59,10 +59,6 @@ def main():
             if t[160 + 3 * i]:
                 e0, e1 = rel(t[400 + 2 * i]), rel(t[401 + 2 * i])
                 print(f"   {i:3d}: {rel(t[160 + 3 * i]):8d} {rel(t[161 + 3 * i]):8d} {rel(t[162 + 3 * i]):8d}   | {e0} {e1}")
-        print("epilogue warp 2, tile 1, per batch of 4 items: loads issued / after wait::ld / batch stored")
-        for i in range(24):
-            if t[500 + 4 * i]:
-                print("   %3d: %s" % (i, " ".join(str(rel(t[500 + 4 * i + k])) for k in range(3))))
 
 
 if __name__ == "__main__":

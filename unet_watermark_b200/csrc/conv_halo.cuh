@@ -497,6 +497,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         else if (p.res) run_items(F_{}, T_{}, F_{});
         else run_items(F_{}, F_{}, F_{});
       }
+      // every tcgen05.ld of this accumulator set has completed (tcgen05.wait::ld above): hand the set back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar(acc));
