@@ -249,7 +249,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
 
   // ---- tile selection: N tile (bn) x sub-tiles per tile (tg), by a small cost model (cycles) ----------
   //   issue  : the one MMA-issuing thread: ~60 instr per stage + ~12 per tap + ~3 per MMA, ~6 clk each (ncu)
-  //   tensor : tg * nk * (kc/16) MMAs of max(32, bn/2) clk   (M=128: 32-clk floor below N=64)
+  //   tensor : tg * nk * (kc/16) MMAs of 32 + bn/4 clk (bn <= 128; 128 clk at bn = 256), measured
   //   L2     : halo(tg)*cin*2 + (weights streamed ? bn*K*2 : 0) bytes per tile; ~64 B/clk per SM, 6300 B/clk chip
   // epilogue staging for TMA tensor stores (8 warps x 32 rows x 128 B): outputs with a multiple of 64 channels
   static const bool ep_tma_enabled = []{ const char* e = getenv("UWM_EP_TMA"); return !(e && e[0] == '0'); }();
@@ -288,7 +288,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const long long tiles = (long long)((s.w + kHaloTW * tg - 1) / (kHaloTW * tg)) * ((s.h + kHaloTH - 1) / kHaloTH) * s.n * n_tiles;
       const long long waves = (tiles + sms - 1) / sms;
       const double mmas = (double)tg * nk * (kc / 16);
-      const double tensor = mmas * std::max(32, bn / 2);
+      const double tensor = mmas * (bn >= 256 ? 128.0 : 32.0 + bn / 4.0);   // measured: operand fetch (128+N)x32 B at 128 B/clk
       const double issue = 6.0 * (60.0 * a.chunks + 12.0 * nk + 3.0 * mmas);
       const double a_bytes = (double)halo_npix(tg, kh, kw) * cin_total * 2;
       const double b_bytes = resident ? 0.0 : (double)bn * nk * kc * 2;
