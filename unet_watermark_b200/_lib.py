@@ -12,7 +12,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libuwm_b200.so")
+LIB_PATH = os.environ.get("UWM_LIB_PATH") or os.path.join(_HERE, "lib", "libuwm_b200.so")   # override: A/B of two builds
 
 IN_F32_NCHW = 0
 IN_U8_NHWC = 1
