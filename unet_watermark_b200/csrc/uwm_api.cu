@@ -759,6 +759,8 @@ struct Op {
   TRef in, in2, out, res;     // in2: second conv source (skip), concatenated after `in` along channels
   bool has_res = false, has_in2 = false;
   bool up = false;            // `in` is nearest-2x upsampled on the fly (decoder conv1)
+  bool side = false;          // independent of its neighbour in op order (downsample conv): forked graph branch
+  bool join = false;          // first consumer of a side-branch result
   int layer = -1;
   double flops_per_img = 0, bytes_per_img = 0;
 };
@@ -776,6 +778,7 @@ struct Launch {          // one kernel of an instantiated plan
   const void* src = nullptr; void* dst = nullptr;
   int n = 0, h = 0, w = 0, c = 0;
   long long src_pitch = 0, dst_pitch = 0;
+  bool side = false, join = false;
 };
 struct GraphKey {        // caller-owned arguments baked into a captured forward
   const void* in; const void* logits; const void* mask; int in_fmt, apply_sigmoid; uint32_t thr_bits;
@@ -803,7 +806,8 @@ struct uwm_model {
   uint8_t* arena = nullptr;
   double flops_per_img = 0;
   std::map<int, Plan> plans;
-  cudaStream_t cap_stream = nullptr;
+  cudaStream_t cap_stream = nullptr, side_stream = nullptr;   // capture streams (main + forked branch)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   int new_buf(size_t bytes_per_img) {
     Buf b; b.bytes_per_img = (bytes_per_img + 1023) & ~(size_t)1023;
@@ -936,6 +940,7 @@ static int build_plan(uwm_model* m) {
         TRef ds = m->dense(oh, ow, out_c);
         int ld = add_layer(m, pre + ".downsample.0", pre + ".downsample.1", cur_c, out_c, 1, stride, 0, 0, 0);
         add_conv(m, ld, x, ds, nullptr);
+        m->ops.back().side = true;      // reads only x: runs beside the block's first conv in the captured graph
         identity = ds;
       }
       if (!r50) {
@@ -944,6 +949,7 @@ static int build_plan(uwm_model* m) {
         add_conv(m, l1, x, t1, nullptr);
         int l2 = add_layer(m, pre + ".conv2", pre + ".bn2", planes[li], planes[li], 3, 1, 1, 1, 1);
         add_conv(m, l2, t1, out, &identity);
+        m->ops.back().join = need_ds;
       } else {  // torchvision Bottleneck v1.5: stride on the 3x3
         TRef t1 = m->dense(cur_h, cur_w, planes[li]);
         int l1 = add_layer(m, pre + ".conv1", pre + ".bn1", cur_c, planes[li], 1, 1, 0, 1, 0);
@@ -953,6 +959,7 @@ static int build_plan(uwm_model* m) {
         add_conv(m, l2, t1, t2, nullptr);
         int l3 = add_layer(m, pre + ".conv3", pre + ".bn3", planes[li], out_c, 1, 1, 0, 1, 1);
         add_conv(m, l3, t2, out, &identity);
+        m->ops.back().join = need_ds;
       }
       x = out; cur_c = out_c; cur_h = oh; cur_w = ow;
     }
@@ -1036,6 +1043,9 @@ extern "C" int uwm_model_create(int encoder, const int* decoder_channels, int h,
     delete m; return rc;
   }
   e = cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { rc = fail(UWM_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); cudaFree(m->arena); delete m; return rc; }
   *out = m;
   return UWM_OK;
@@ -1047,6 +1057,9 @@ extern "C" int uwm_model_destroy(uwm_model* m) {
   for (auto& L : m->layers) { if (L.d_w) cudaFree(L.d_w); if (L.d_b) cudaFree(L.d_b); }
   if (m->arena) cudaFree(m->arena);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->side_stream) cudaStreamDestroy(m->side_stream);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   delete m;
   return UWM_OK;
 }
@@ -1082,6 +1095,7 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
   for (const Op& op : m->ops) {
     Launch L;
     L.type = op.type;
+    L.side = op.side; L.join = op.join;
     switch (op.type) {
       case OP_PREP:
         L.src = d_in; L.dst = m->ptr(op.out); L.n = batch; L.h = m->H; L.w = m->W; L.c = in_fmt;
@@ -1193,10 +1207,25 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
     if (rc) return rc;
     cudaGraph_t g = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed));
+    // The downsample conv of a residual stage reads only the block input: it is captured on a forked stream so the
+    // graph runs it beside the block's first conv, and joined before the conv that adds it as the residual.
+    static const bool fork_side = []{ const char* e = getenv("UWM_FORK"); return !(e && e[0] == '0'); }();
+    bool pending_join = false;
     for (size_t i = 0; i < n; ++i) {
-      rc = run_launch(pl.launches[i], m->cap_stream);
+      const Launch& L = pl.launches[i];
+      if (L.side && fork_side) {
+        cudaEventRecord(m->ev_fork, m->cap_stream);
+        cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0);
+        rc = run_launch(L, m->side_stream);
+        cudaEventRecord(m->ev_join, m->side_stream);
+        pending_join = true;
+      } else {
+        if (L.join && pending_join) { cudaStreamWaitEvent(m->cap_stream, m->ev_join, 0); pending_join = false; }
+        rc = run_launch(L, m->cap_stream);
+      }
       if (rc) { cudaStreamEndCapture(m->cap_stream, &g); if (g) cudaGraphDestroy(g); return rc; }
     }
+    if (pending_join) cudaStreamWaitEvent(m->cap_stream, m->ev_join, 0);
     CUDA_TRY(cudaStreamEndCapture(m->cap_stream, &g));
     cudaGraphExec_t exec = nullptr;
     cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
