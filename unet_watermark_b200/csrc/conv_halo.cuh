@@ -162,7 +162,7 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
-                 const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+                 const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                  const __grid_constant__ HaloKArgs p) {
   constexpr int NT = KH * KW;
   constexpr int CPS = KC / 8;                               // 8-channel planes per stage
@@ -199,10 +199,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   auto accf_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + a); };
   auto acce_bar = [&](int a) { return bar_base + 8u * (4 * kHaloMaxStages + 4 + a); };
   const uint32_t bres_bar = bar_base + 8u * (4 * kHaloMaxStages + 8);
+  auto resbar = [&](int w) { return bar_base + 8u * (4 * kHaloMaxStages + 12 + w); };   // residual box landed (per epilogue warp)
   uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 10));
   // folded-BN bias of every output channel, staged once: the epilogue re-reads it per 16-column chunk, and the
   // trace showed that re-read missing L1 (an L2 round trip of 500-800 cycles in front of the first FADD)
-  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 12));
+  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 20));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,9 +216,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
     for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
     mbar_init(bres_bar, 1);
+    for (int w = 0; w < 8; ++w) mbar_init(resbar(w), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
-    if (p.ep_tma) tma_prefetch_desc(&tm_out);
+    if (p.ep_tma) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
     if (A_TMA) { tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); }
   }
   if (warp == 1) {
@@ -364,6 +366,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     // 128B swizzle of the 16-byte chunks of this lane's row: chunk index ^ (row & 7)
     const uint32_t my_row_off = (uint32_t)lane * 128u;
     const uint32_t sw_xor = (uint32_t)lane & 7u;
+    uint32_t res_cnt = 0;                      // residual boxes consumed by this warp (barrier parity)
     pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
@@ -375,6 +378,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       const bool row_ok = oh < p.h;
       const long long pix0 = ((long long)t.img * p.h + oh) * p.w + ow0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (TG * bn);
+
+      // Residual convs with staged TMA stores: the residual box of the warp's first (sub-tile, 64 channels) unit is
+      // TMA-loaded into the warp's staging buffer NOW, long before the accumulator is complete; the epilogue adds it
+      // in place.  (Lane-per-pixel global loads exposed an L2 round trip per 16-column item in the drain.)
+      const bool res_tma = tma_out && (p.res != nullptr) && !(p.dbg & 4);
+      if (res_tma && lane == 0 && c_first * 4 < min(p.block_n, p.cout - col0)) {
+        bulk_wait_read<0>();                 // the previous tile's last store has read the buffer out
+        mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
+        tma_load_4d(stg, &tm_res, resbar(ewarp), col0 + c_first * 4, t.w0 + g_first * kHaloTW, t.h0 + q * 4, t.img);
+      }
 
       if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> nacc_log2) & 1u);
       __syncwarp();
@@ -421,7 +434,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             auto item_load = [&](int n, int b) {
               const int g = GSTEP * (n >> LOG2_JN) + g_first, c = cg0 + ((n & (JN - 1)) << 4);
               tmem_ld_x16(taddr0 + (uint32_t)g * bn + c, v[b]);
-              if (RES) {
+              if (RES && !TMA) {
                 r0[b] = make_uint4(0, 0, 0, 0); r1[b] = make_uint4(0, 0, 0, 0);
                 if (row_ok && (ow0 + g * kHaloTW < p.w)) {
                   r0[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
@@ -449,7 +462,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[u][k]) + bb[k];
                 if (RES) {
-                  const uint32_t rr[8] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w, r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+                  uint4 x0, x1;
+                  if (TMA) {               // residual box of this unit sits in the staging buffer (own row, same swizzle)
+                    if (j == 0) {
+                      if (lane == 0) mbar_wait(resbar(ewarp), res_cnt & 1u);
+                      __syncwarp();
+                      ++res_cnt;
+                    }
+                    x0 = ld_shared_v4(stg + my_row_off + (((uint32_t)(2 * j) ^ sw_xor) << 4));
+                    x1 = ld_shared_v4(stg + my_row_off + (((uint32_t)(2 * j + 1) ^ sw_xor) << 4));
+                  } else {
+                    x0 = r0[u]; x1 = r1[u];
+                  }
+                  const uint32_t rr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                   for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(rr[k]); f[2 * k + 1] += bf16_hi(rr[k]); }
                 }
@@ -461,7 +486,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                 o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
                 o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
                 if (TMA) {
-                  if (j == 0) {          // the previous store of this warp must have read the buffer out
+                  if (j == 0 && !RES) {  // the previous store of this warp must have read the buffer out
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
                   }
@@ -474,6 +499,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                     if (lane == 0) {
                       tma_store_4d(&tm_out, stg, col0 + cg0, t.w0 + g * kHaloTW, t.h0 + q * 4, t.img);
                       bulk_commit();
+                      if (RES) {           // next unit of this tile: its residual box, once the store has read the buffer
+                        const int gi_n = (n >> LOG2_JN) + 1;
+                        const int g_n = (gi_n < GN) ? GSTEP * gi_n + g_first : g_first;
+                        const int cg_n = (gi_n < GN) ? cg0 : cg0 + c_step * JN;
+                        if (cg_n < ncols) {
+                          bulk_wait_read<0>();
+                          mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
+                          tma_load_4d(stg, &tm_res, resbar(ewarp), col0 + cg_n, t.w0 + g_n * kHaloTW, t.h0 + q * 4, t.img);
+                        }
+                      }
                     }
                   }
                 } else if (SHUF) {

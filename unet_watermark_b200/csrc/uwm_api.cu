@@ -149,7 +149,7 @@ struct ConvSpec {
 struct ConvLaunch {
   int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
   int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0;   // halo: template instantiation
-  CUtensorMap tm_act, tm_wgt, tm_out, tm_a0, tm_a1;
+  CUtensorMap tm_act, tm_wgt, tm_out, tm_res, tm_a0, tm_a1;
   ConvKArgs args;
   HaloKArgs hargs;
   unsigned grid = 0;
@@ -395,8 +395,18 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     if (r != CUDA_SUCCESS)
       return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(out) -> %d (c=%d w=%d h=%d n=%d pitch=%lld)", (int)r, s.cout, s.w, s.h,
                   s.n, s.out_pitch);
+    L->tm_res = L->tm_out;
+    if (s.res) {              // residual view with the same boxes (added in place in the staging buffer)
+      cuuint64_t rstr[3] = {(cuuint64_t)s.res_pitch * 2, (cuuint64_t)s.w * s.res_pitch * 2,
+                            (cuuint64_t)s.h * s.w * s.res_pitch * 2};
+      r = enc(&L->tm_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.res), odims, rstr, obox, oest,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(res) -> %d", (int)r);
+    }
   } else {
     L->tm_out = L->tm_wgt;    // unused by the kernel
+    L->tm_res = L->tm_wgt;
   }
   L->tm_a0 = L->tm_wgt; L->tm_a1 = L->tm_wgt;
   if (a_tma) {
@@ -555,7 +565,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES &&           \
              (L->a_tma != 0) == AT) {                                                                           \
     launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
-               L->tm_a0, L->tm_a1, L->hargs);                                                                   \
+               L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                                                   \
     return UWM_OK;                                                                                              \
   }
 #define UWM_HALO_CASE(KC, KH, KW, TG, RES) UWM_HALO_CASE1(KC, KH, KW, TG, RES, false) UWM_HALO_CASE1(KC, KH, KW, TG, RES, true)
