@@ -1,5 +1,6 @@
-// Halo-resident implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) for stride-1 k x k convs,
-// with the decoder's nearest-2x upsample and skip concat fused into the activation loader.
+// Halo-resident implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) for stride-1 k x k convs
+// (3x3, the stem's 4x4 over the space-to-depth input, 1x1), with the decoder's nearest-2x upsample and
+// skip concat fused into the activation loader, and a sub-pixel mode for the skip-less decoder conv.
 //
 //   out[n,h,w,co] = epilogue( sum_{tap,ci} in[n, h+dh(tap), w+dw(tap), ci] * wgt[co, tap, ci] )
 //   in = concat_c( up2x?(src0), src1 )          (src1 optional; up2x = F.interpolate(nearest, x2))
@@ -8,29 +9,32 @@
 // filter tap (9x for a 3x3), and the L2->SM fabric (~42 B/clk/SM) - not the tensor pipe - bounds every
 // layer.  Here a CTA loads the HALO of its output tile ONCE per 64-channel chunk and every tap reads a
 // shifted window of that one copy.  A tile is TG sub-tiles of 8 (w) x 16 (h) pixels side by side; each
-// sub-tile is one M=128 accumulator, all of them share the halo and every weight slice:
+// sub-tile is one M=128 accumulator, all of them share the halo and every weight slice.
 //
-//   smem A stage = [kc/8 channel groups][halo pixels][8 channels = 16 B]      (no-swizzle K-major)
-//     core matrix  = 8 consecutive pixels x 16 B = 128 contiguous bytes
-//     SBO (8-row group stride, M direction) = halo_width * 16 B   -> next image row of the tile
-//     LBO (core-matrix stride, K direction) = plane_bytes         -> next 8-channel group
-//     tap (r,c), sub-tile g: descriptor start address += (r*halo_width + c + 8*g) * 16 B
+// A operand, two layouts (template A_TMA):
+//   A_TMA (all sources at the conv's resolution): ONE TMA box per stage - KC channels x halo_w x halo_h
+//     pixels, out-of-image coordinates zero-filled (= conv padding) - in the 128B/64B/32B-swizzled
+//     pixel-major layout (row = pixel, KC*2 bytes).  Tap (r,c), sub-tile g: descriptor start address
+//     += (r*halo_w + c + 8g) rows; SBO = halo_w rows.  A start that is not aligned to the 8-row swizzle
+//     atom still reads what TMA wrote: both units derive the XOR from the absolute smem address.
+//   !A_TMA (an upsampled source): loader warps gather 16-byte pieces with cp.async (zero-fill = padding;
+//     source pixel (h>>1, w>>1) for the upsampled source) into a no-swizzle K-major layout
+//     [kc/8 channel groups][halo pixels][16 B]: SBO = halo_w*16 B, LBO = plane stride, start address
+//     += (r*halo_w + c + 8g)*16 B; completion -> mbarrier through cp.async.mbarrier.arrive.  Neither the
+//     upsampled tensor nor the concat ever exists in HBM.
+// B operand (weights): TMA into 128B/64B/32B-swizzled K-major slices, resident in smem for the small layers
+// or streamed through their own ring.
 //
-// Loader warps fill a stage with 16-byte cp.async (zero-fill outside the image = conv padding; the
-// source pixel is (h>>1, w>>1) for an upsampled source, so neither the upsampled tensor nor the concat
-// ever exists in HBM) and signal an mbarrier through cp.async.mbarrier.arrive.  Weights take the same
-// route as in conv_tc.cuh: TMA into 128B/64B/32B-swizzled K-major slices, resident in smem for the small
-// layers or streamed through their own ring.
-//
-// Filter shape, TG and the weight mode are template parameters: ncu shows the single MMA-issuing thread is
-// the critical resource of the small layers (9 MMAs of 32 cycles per 128 pixels against ~350 issue-side
-// instructions per tile in a generic loop), so its loop is fully unrolled with immediate descriptor offsets
-// and TG sub-tiles share every wait/commit.
+// Filter shape, TG and the weight mode are template parameters: ncu and the in-kernel trace show a warp
+// running ~4-10 cycles per instruction in these role loops, so the single MMA-issuing thread (9 MMAs of 32
+// cycles per 128 pixels in the smallest layers) and the epilogue are instruction-count bound unless their
+// loops are fully unrolled with immediate offsets; the epilogue's item loop is instantiated per output mode.
 //
 // Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0      weight TMA producer          warp 1    TMEM owner + tcgen05.mma issuer
-//   warps 2-5   epilogue set 0 (TMEM -> bias/residual/ReLU -> bf16 NHWC, or head: logits / uint8 mask)
-//   warps 6-9   activation loaders
+//   warps 2-5   epilogue set 0 (TMEM -> bias/residual/ReLU -> bf16 NHWC through a swizzled smem staging row and
+//               a TMA tensor store, or direct stores for 16/32 channels, or head: logits / uint8 mask)
+//   warps 6-9   activation loaders (one elected thread when A_TMA)
 //   warps 10-13 epilogue set 1: a warp may only read TMEM lanes 32*(warp%4).., and one warp per lane quarter
 //               is latency-bound (one TMEM load -> math -> store chain at a time), so every quarter gets two
 //               warps that split the sub-tiles (or the 16-column chunks when TG == 1) of each tile
