@@ -101,6 +101,7 @@ struct HaloKArgs {
   float* logits;
   uint8_t* mask;
   float thr_logit;
+  int mix;                                  // !A_TMA kernels: chunks of src[1] arrive as TMA boxes (swizzled stage layout)
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
   int shuffle;                              // > 0: sub-pixel mode, real cout; GEMM column n = parity*shuffle + co is stored to
                                             // pixel (2h + parity/2, 2w + parity%2), channel co of the 2x larger output (pixel shuffle)
@@ -180,7 +181,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   // derive the swizzle XOR from the absolute shared-memory address, so a start address that is not aligned to
   // the 8-row swizzle atom still reads what TMA wrote.
   constexpr uint32_t ROWB = KC * 2;
-  constexpr uint32_t A_STAGE_BYTES = A_TMA ? ((uint32_t)NPIX * ROWB + 1023u) & ~1023u : CPS * PLANE_BYTES;
+  constexpr uint32_t A_SW_BYTES = ((uint32_t)NPIX * ROWB + 1023u) & ~1023u;
+  constexpr uint32_t A_PL_BYTES = (CPS * PLANE_BYTES + 1023u) & ~1023u;     // !A_TMA stages may hold either layout
+  constexpr uint32_t A_STAGE_BYTES = A_TMA ? A_SW_BYTES : (A_SW_BYTES > A_PL_BYTES ? A_SW_BYTES : A_PL_BYTES);
   constexpr int ITEMS = NPIX * CPS;                         // 16-byte pieces per stage
   constexpr uint32_t B_LAYOUT = (KC == 64) ? kLayoutSw128 : (KC == 32) ? kLayoutSw64 : kLayoutSw32;
 
@@ -225,6 +228,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     tma_prefetch_desc(&tm_wgt);
     if (p.ep_tma) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
     if (A_TMA) { tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); }
+    else if (p.mix) tma_prefetch_desc(&tm_a1);
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(s_tmem_slot), p.tmem_cols);
@@ -275,11 +279,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one elected thread)
     const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
-    // A: no-swizzle K-major.  hi = SBO (halo row) | version;  lo = start>>4 | LBO (plane stride) << 16
-    constexpr uint32_t a_hi = A_TMA ? (((uint32_t)PW * ROWB) >> 4) | (1u << 14) | (B_LAYOUT << 29) : (uint32_t)PW | (1u << 14);
-    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | ((A_TMA ? 1u : PLANE_UNITS) << 16);
-    constexpr uint32_t a_px_units = A_TMA ? (ROWB >> 4) : 1u;      // 16-byte units per halo pixel step
-    constexpr uint32_t a_k_units = A_TMA ? 2u : 2u * PLANE_UNITS;   // 16-byte units per K=16 slice
+    // A descriptors, per stage layout.  swizzled pixel-major (TMA box): hi = SBO (one halo row) | version | swizzle,
+    // LBO unused.  no-swizzle planes (cp.async gather): hi = SBO (halo_w x 16 B) | version, LBO = plane stride.
+    constexpr uint32_t a_hi_sw = (((uint32_t)PW * ROWB) >> 4) | (1u << 14) | (B_LAYOUT << 29);
+    constexpr uint32_t a_hi_pl = (uint32_t)PW | (1u << 14);
+    const uint32_t a_lo0_sw = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_lo0_pl = ((a_base & 0x3FFFFu) >> 4) | (PLANE_UNITS << 16);
     constexpr uint32_t a_stage_units = A_STAGE_BYTES >> 4;
     // B: swizzled K-major slices, rows of KC*2 bytes
     constexpr uint32_t b_hi = ((8u * KC * 2u) >> 4) | (1u << 14) | (B_LAYOUT << 29);
@@ -304,10 +309,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           if (ch == 0) halo_trace(p, 161 + 3 * it);
           if (!A_TMA) fence_proxy_async_smem();        // loaders wrote through the generic proxy (cp.async)
           tc_fence_after();
-          const uint32_t a_st = a_lo0 + (uint32_t)sa * a_stage_units;
           uint32_t b_lo = b_lo0 + (uint32_t)(ch * NT) * b_slice_units;   // resident: slice (ch, tap 0)
           int j = 0;                                                      // streamed: slice inside the stage
-          if (!skip_mma) {
+          // one K chunk: all taps x sub-tiles x K=16 slices, instantiated per stage layout (immediate offsets)
+          auto issue_chunk = [&](auto swz_c) {
+            constexpr bool SWZ = decltype(swz_c)::value;
+            constexpr uint32_t a_hi = SWZ ? a_hi_sw : a_hi_pl;
+            constexpr uint32_t a_px_units = SWZ ? (ROWB >> 4) : 1u;       // 16-byte units per halo pixel step
+            constexpr uint32_t a_k_units = SWZ ? 2u : 2u * PLANE_UNITS;   // 16-byte units per K=16 slice
+            const uint32_t a_st = (SWZ ? a_lo0_sw : a_lo0_pl) + (uint32_t)sa * a_stage_units;
 #pragma unroll
             for (int tap = 0; tap < NT; ++tap) {
               const uint32_t shift = (uint32_t)((tap / KW) * PW + (tap % KW));
@@ -335,6 +345,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                 if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
               }
             }
+          };
+          if (!skip_mma) {
+            if (A_TMA) issue_chunk(std::true_type{});
+            else if (p.mix && ch >= p.split_chunk) issue_chunk(std::true_type{});    // skip source: TMA box
+            else issue_chunk(std::false_type{});                                     // upsampled source: gather
           } else if (!RESIDENT) {
             for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
               mbar_wait_fast(bfull_bar(sb), phb);
@@ -588,6 +603,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         __syncwarp();
         if (lt == 0) halo_trace(p, 16 + 2 * nstage);
         const uint32_t dst0 = a_base + (uint32_t)s * A_STAGE_BYTES;
+        if (p.mix && ch >= p.split_chunk && !(p.dbg & 1)) {
+          // the skip source is stored at the conv's resolution: one TMA box (swizzled layout) instead of a gather;
+          // the barrier expects one arrival per loader thread, so thread 0's expect_tx arrival is one of them
+          if (lt == 0) {
+            mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
+            tma_load_4d(dst0, &tm_a1, afull_bar(s), (ch - p.split_chunk) * KC, wbase, hbase, t.img);
+          } else {
+            mbar_arrive(afull_bar(s));
+          }
+          if (lt == 0) halo_trace(p, 17 + 2 * nstage);
+          ++nstage;
+          if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+          continue;
+        }
         if (!(p.dbg & 1)) {
 #pragma unroll 4
           for (int i = lt; i < ITEMS; i += kHaloLoaderThreads) {

@@ -261,8 +261,10 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   static const bool a_tma_enabled = []{ const char* e = getenv("UWM_A_TMA"); return !(e && e[0] == '0'); }();
   const bool a_tma = a_tma_enabled && !s.up1;
   auto a_stage_of = [&](int tg) -> size_t {
-    if (a_tma) return (((size_t)halo_npix(tg, kh, kw) * kc * 2) + 1023) & ~(size_t)1023;
-    return (size_t)cps * halo_plane_bytes(tg, kh, kw);
+    const size_t sw = (((size_t)halo_npix(tg, kh, kw) * kc * 2) + 1023) & ~(size_t)1023;
+    if (a_tma) return sw;
+    const size_t pl = ((size_t)cps * halo_plane_bytes(tg, kh, kw) + 1023) & ~(size_t)1023;
+    return std::max(sw, pl);          // a gathered stage (planes) or a TMA box of the skip source (swizzled rows)
   };
   struct Cand { int bn, tg; bool resident; double cost; } best = {0, 0, false, 1e30};
   std::vector<int> bns;
@@ -358,6 +360,8 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
   { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.trace = g_halo_trace;
+  { static const bool mix_on = []{ const char* e = getenv("UWM_MIX"); return !(e && e[0] == '0'); }();
+    a.mix = (!a_tma && s.x2 && mix_on) ? 1 : 0; }
   { const char* e = getenv("UWM_TRACE_KH"); if (e && atoi(e) != kh) a.trace = nullptr; }   // bench-only: trace one filter shape
   a.shuffle = s.shuffle;
   a.ep_tma = ep_tma ? 1 : 0; a.ep_cols = ep_tma ? 64 : 16;
@@ -409,8 +413,8 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     L->tm_res = L->tm_wgt;
   }
   L->tm_a0 = L->tm_wgt; L->tm_a1 = L->tm_wgt;
-  if (a_tma) {
-    for (int i = 0; i < 2; ++i) {
+  if (a_tma || s.x2) {                  // !a_tma with a skip source: only the skip source's box map is used (mix)
+    for (int i = a_tma ? 0 : 1; i < 2; ++i) {
       if (i == 1 && !s.x2) { L->tm_a1 = L->tm_a0; break; }
       const void* base = i ? s.x2 : s.x;
       const long long pitch = i ? s.x2_pitch : s.x_pitch;
