@@ -46,6 +46,15 @@ extern "C" {
                                  [4*cout][3*3][cin] bf16, row (ph*2+pw)*cout + co, tap (a,b) holds the SUM (in fp32,
                                  rounded once) of w[co,:,dy,dx] over the taps with floor((ph+dy-1)/2) == a-1 and
                                  floor((pw+dx-1)/2) == b-1; bias = 4 copies (packing.pack_up2x_shuffle)          */
+#define UWM_PACK_UPCAT_SUBPIXEL 3 /* conv3x3 over concat(nearest-2x(x), skip) as a sub-pixel conv on x's grid, weight
+                                 slices of 64 input channels in issue order, rows (qh*2+qw)*cout + co:
+                                 per 64-channel chunk of x the 9 UWM_PACK_UP2X_SHUFFLE taps, centre tap first, then
+                                 row-major; then per parity plane
+                                 (ph,pw) of skip, per 64-channel chunk, the taps r in {1-ph,2-ph} x c in {1-pw,2-pw}
+                                 holding w[co, c_x + ci, 2(r-1)+ph-qh+1, 2(c-1)+pw-qw+1] (zero when out of the
+                                 3x3 kernel); bias = 4 copies (packing.pack_upcat_subpixel).  Tap row 0 / 2 of the
+                                 block neighbourhood only reaches qh = 0 / 1 (same for columns): the kernel loads
+                                 and multiplies only those rows of such a slice                                   */
 #define UWM_PACK_STEM_S2D 1   /* 7x7/s2 stem as 4x4/s1 over the 2x2 space-to-depth input:
                                  [64][4*4][16] bf16, channel = (ph*2+pw)*3 + c, 12..15 zero      */
 
@@ -98,6 +107,16 @@ int uwm_conv2d_up2x_shuffle_nhwc_bf16(const void* d_x, int n, int h, int w, int 
                                       const void* d_wgt /*[4*cout][9*cin]*/, const float* d_bias /*[4*cout]*/,
                                       int cout, int relu, void* d_y, int y_pitch, void* stream);
 
+/* The same sub-pixel form for the decoder conv1 WITH a skip: y = act(conv3x3(concat(nearest-2x(x), skip)) + bias).
+ * x[n,h,w,c_x]; skip[n,2h,2w,c_skip]; y[n,2h,2w,cout]; c_x and c_skip multiples of 64, cout a multiple of 16, <= 64.
+ * wgt: UWM_PACK_UPCAT_SUBPIXEL.  The skip source is read as four parity planes (TMA boxes with element stride 2);
+ * plane (ph,pw) meets only the 2x2 taps that can reach it.  Replaces segmentation_models_pytorch
+ * decoders/unet/decoder.py DecoderBlock.forward (interpolate + cat + conv1) for blocks with a skip. */
+int uwm_conv2d_upcat_subpixel_nhwc_bf16(const void* d_x, int n, int h, int w, int c_x, int x_pitch,
+                                        const void* d_skip, int c_skip, int skip_pitch, const void* d_wgt,
+                                        const float* d_bias, int cout, int relu, void* d_y, int y_pitch,
+                                        void* stream);
+
 /* Segmentation head: conv3x3(cin -> 1, bias) + optional sigmoid + threshold + uint8 mask.
  * Replaces smp SegmentationHead and `(mask > thr)*255`
  * (reference src/predict.py:624-625).  d_logits (fp32 [n,h,w]) and d_mask (uint8 [n,h,w],
@@ -135,6 +154,8 @@ typedef struct uwm_layer_desc {
   int64_t w_elems;        /* bf16 elements expected by uwm_model_set_layer                   */
   int64_t b_elems;        /* fp32 elements expected                                           */
   double  flops_per_image;/* 2*MACs of the reference conv (algorithmic, un-padded)            */
+  int32_t cin_skip;       /* UWM_PACK_UPCAT_SUBPIXEL: channels of the skip source (last cin_skip of cin) */
+  int32_t reserved;
 } uwm_layer_desc;
 
 /* encoder: 34 or 50.  decoder_channels: 5 ints (smp default 256,128,64,32,16).

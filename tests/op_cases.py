@@ -69,3 +69,14 @@ SHUFFLE_CASES = [
     ("subpixel_64",           1, 16, 16, 64, 64, True),      # 4*64 = 256 GEMM columns (two N tiles possible)
     ("subpixel_persistent",   2, 128, 128, 32, 16, True),
 ]
+
+# Sub-pixel form of conv3x3(cat(nearest_up2x(x), skip)) - uwm_conv2d_upcat_subpixel_nhwc_bf16.
+# (name, n, h_lo, w_lo, c_x, c_skip, cout, relu)
+SPX_CASES = [
+    ("d3_up64_skip64_32_spx",  1, 32, 32, 64, 64, 32, True),       # the r34 decoder block 3 shape (two sub-tiles)
+    ("spx_ragged",             2, 12, 20, 64, 64, 32, False),      # 24x40 output: partial tiles on both axes
+    ("spx_narrow_tg1",         1, 16, 8, 64, 128, 16, True),       # one sub-tile per tile, N = 64, two skip chunks
+    ("spx_two_x_chunks",       1, 16, 16, 128, 64, 32, True),      # r34 decoder block 2 channels at cout 32
+    ("spx_n256",               1, 16, 32, 128, 64, 64, True),      # N = 256 (one sub-tile, 2 x 256 TMEM columns)
+    ("spx_persistent",         2, 128, 128, 64, 64, 32, True),     # several tiles per CTA
+]

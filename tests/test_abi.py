@@ -39,8 +39,8 @@ def test_binding_table_matches_header():
 
 
 def test_layer_desc_struct_matches_header_layout():
-    # char[96]*2 + 10*int32 + 2*int64 + double
-    assert ctypes.sizeof(_lib.LayerDesc) == 96 * 2 + 10 * 4 + 2 * 8 + 8
+    # char[96]*2 + 10*int32 + 2*int64 + double + 2*int32 (cin_skip, reserved)
+    assert ctypes.sizeof(_lib.LayerDesc) == 96 * 2 + 10 * 4 + 2 * 8 + 8 + 2 * 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")

@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.op_cases import CONV_CASES, SHUFFLE_CASES, UPCAT_CASES
+from tests.op_cases import CONV_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES
 from unet_watermark_b200 import _lib, ops, packing
 
 pytestmark = pytest.mark.gpu
@@ -92,6 +92,32 @@ def test_subpixel_conv_matches_fp32_reference(case, cuda_device):
     assert out.shape == (n, 2 * h, 2 * w, cout)
     xi = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
     ref = F.conv2d(xi, wt.to(torch.bfloat16).float(), bias, padding=1)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1.5e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+
+
+@pytest.mark.parametrize("case", SPX_CASES, ids=[c[0] for c in SPX_CASES])
+def test_upcat_subpixel_conv_matches_fp32_reference(case, cuda_device):
+    """conv3x3(cat(interpolate(x, 2, nearest), skip)) computed on x's grid (x taps pre-summed, skip read as four parity
+    planes with 2x2 taps each, pixel-shuffle epilogue) vs the torch ops on the ORIGINAL bf16-rounded weights.
+    Tolerance: the per-op one plus one extra weight rounding of the pre-summed x taps, 1.5e-2 * max(1, |ref|)."""
+    name, n, h, w, cx, cs, cout, relu = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(n, h, w, cx, generator=g).to(dev).to(torch.bfloat16)
+    skip = torch.randn(n, 2 * h, 2 * w, cs, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cx + cs, 3, 3, generator=g) / ((cx + cs) * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    ws = packing.pack_upcat_subpixel(wt, cx)
+    before = _lib.load().uwm_kernel_launch_count()
+    out = ops.conv2d_upcat_subpixel(x, skip, ws, bias.repeat(4).contiguous(), relu=relu)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    assert out.shape == (n, 2 * h, 2 * w, cout)
+    xi = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(torch.cat([xi, skip.float().permute(0, 3, 1, 2)], 1), wt.to(torch.bfloat16).float(), bias, padding=1)
     if relu:
         ref = ref.relu()
     ref = ref.permute(0, 2, 3, 1)

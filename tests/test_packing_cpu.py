@@ -63,3 +63,61 @@ def test_subpixel_packing_equals_conv_on_upsampled_input():
     wp = packing.pack_up2x_shuffle(w).float()
     assert wp.shape == (4 * cout, 9 * cin)
     assert torch.equal(wp, out.reshape(4 * cout, 9 * cin).to(torch.bfloat16).float())
+
+
+def _emulate_upcat_subpixel(x, skip, wp, c_x, cout):
+    """What the SPX kernel computes from UWM_PACK_UPCAT_SUBPIXEL weights, restated with torch slicing: x chunks meet
+    all 9 taps of x's zero-padded halo, parity plane (ph,pw) of skip meets taps {1-ph,2-ph} x {1-pw,2-pw} of ITS halo,
+    and GEMM column (qh*2+qw)*cout + co of source pixel (i,j) lands on output pixel (2i+qh, 2j+qw)."""
+    n, _, h, w = x.shape
+    c_s = skip.shape[1]
+    acc = torch.zeros(n, 4 * cout, h, w)
+    k = 0
+
+    def mac(a_halo, r, c):
+        nonlocal k
+        sl = wp[:, k * 64:(k + 1) * 64]
+        k += 1
+        # the kernel only loads the rows tap (r,c) can reach: all (r == 1), the qh half (c == 1) or one parity group
+        qn = 4 if r == 1 else (2 if c == 1 else 1)
+        qoff = 0 if r == 1 else 2 * (r == 2) + (0 if c == 1 else (c == 2))
+        rows = slice(qoff * cout, (qoff + qn) * cout)
+        rest = torch.ones(4 * cout, dtype=torch.bool)
+        rest[rows] = False
+        assert not sl[rest].any(), "rows outside the tap's reach must be structurally zero"
+        acc[:, rows].add_(torch.einsum("ok,nkhw->nohw", sl[rows], a_halo[:, :, r:r + h, c:c + w]))
+
+    for ch in range(c_x // 64):
+        halo = F.pad(x[:, ch * 64:(ch + 1) * 64], (1, 1, 1, 1))
+        for tap in packing.SPX_X_TAP_ORDER:
+            mac(halo, tap // 3, tap % 3)
+    for ph in range(2):
+        for pw in range(2):
+            for cc in range(c_s // 64):
+                halo = F.pad(skip[:, cc * 64:(cc + 1) * 64, ph::2, pw::2], (1, 1, 1, 1))
+                for r in (1 - ph, 2 - ph):
+                    for c in (1 - pw, 2 - pw):
+                        mac(halo, r, c)
+    assert k * 64 == wp.shape[1]
+    y = acc.reshape(n, 2, 2, cout, h, w)                                   # [n, qh, qw, co, i, j]
+    return y.permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
+
+
+def test_upcat_subpixel_packing_equals_conv_on_upsample_concat():
+    """conv3x3(cat(nearest_up2x(x), skip)) == the sub-pixel GEMM over x's grid with parity planes of skip."""
+    g = torch.Generator().manual_seed(3)
+    for cout, c_x, c_s, h, w in ((16, 64, 64, 5, 6), (32, 128, 64, 3, 4)):
+        wt = torch.randn(cout, c_x + c_s, 3, 3, generator=g) / ((c_x + c_s) * 9) ** 0.5
+        wt = wt.to(torch.bfloat16).float()
+        x = torch.randn(2, c_x, h, w, generator=g)
+        skip = torch.randn(2, c_s, 2 * h, 2 * w, generator=g)
+        ref = F.conv2d(torch.cat([F.interpolate(x, scale_factor=2, mode="nearest"), skip], 1), wt, padding=1)
+        wp = packing.pack_upcat_subpixel(wt, c_x)
+        assert wp.dtype == torch.bfloat16 and wp.shape == (4 * cout, 64 * (9 * c_x // 64 + 16 * c_s // 64))
+        got = _emulate_upcat_subpixel(x, skip, wp.float(), c_x, cout)
+        # only the pre-summed x taps are re-rounded to bf16 (skip weights are copied bit-exactly)
+        assert torch.allclose(got, ref, atol=2e-2, rtol=0), (got - ref).abs().max()
+        # skip part alone is exact up to fp32 summation order
+        x0 = torch.zeros_like(x)
+        ref0 = F.conv2d(torch.cat([F.interpolate(x0, scale_factor=2, mode="nearest"), skip], 1), wt, padding=1)
+        assert torch.allclose(_emulate_upcat_subpixel(x0, skip, wp.float(), c_x, cout), ref0, atol=1e-4, rtol=1e-4)

@@ -23,6 +23,8 @@ SHAPES = [  # name, n, h, w, cin (x), cskip, cout, upsample
     ("dec1 up256+128->128 @64", 16, 32, 32, 256, 128, 128, True),
     ("dec2 up128+64->64 @128", 16, 64, 64, 128, 64, 64, True),
     ("dec3 up64+64->32 @256", 16, 128, 128, 64, 64, 32, True),
+    ("dec3 spx up64+64->32 @256", 16, 128, 128, 64, 64, 32, "spx"),
+    ("dec2 spx up128+64->64 @128", 16, 64, 64, 128, 64, 64, "spx"),
     ("dec3 32->32 @256", 16, 256, 256, 32, 0, 32, False),
     ("dec4 up32->16 @512", 16, 256, 256, 32, 0, 16, True),
     ("dec4 16->16 @512", 16, 512, 512, 16, 0, 16, False),
@@ -45,21 +47,28 @@ def main():
         ho, wo = (2 * h, 2 * w) if up else (h, w)
         skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
         cin = cx + cs
-        wp = packing.pack_taps(torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5)
-        b = torch.zeros(cout, device=dev)
+        wt = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+        wp = packing.pack_upcat_subpixel(wt, cx) if up == "spx" else packing.pack_taps(wt)
+        b = torch.zeros(4 * cout if up == "spx" else cout, device=dev)
         out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
         times = []
+
+        def run():
+            if up == "spx":
+                ops.conv2d_upcat_subpixel(x, skip, wp, b, relu=True, out=out)
+            else:
+                ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
         for d in dbgs:
             os.environ["UWM_DBG"] = str(d)
             for _ in range(3):
-                ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+                run()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
             if args.graph:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     for _ in range(20):
-                        ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+                        run()
                 g.replay()
                 torch.cuda.synchronize()
                 e0.record()
@@ -70,7 +79,7 @@ def main():
             else:
                 e0.record()
                 for _ in range(10):
-                    ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
+                    run()
                 e1.record()
                 torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1) / 10)

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.op_cases import CONV_CASES, SHUFFLE_CASES, UPCAT_CASES  # noqa: E402
+from tests.op_cases import CONV_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES  # noqa: E402
 from unet_watermark_b200 import ops, packing  # noqa: E402
 
 
@@ -140,6 +140,33 @@ def main():
         except Exception as ex:  # noqa: BLE001
             nfail += 1
             print(f"EXC  subpx {case[0]}: {ex}", flush=True)
+            traceback.print_exc()
+            if "CUDA" in str(ex) or "fault" in str(ex):
+                print("aborting after CUDA error")
+                sys.exit(2)
+
+    for case in SPX_CASES:
+        if args.filter not in case[0]:
+            continue
+        try:
+            name, n, h, w, cx, cs, cout, relu = case
+            g = torch.Generator(device="cpu").manual_seed(0)
+            x = torch.randn(n, h, w, cx, generator=g).to(dev).to(torch.bfloat16)
+            skip = torch.randn(n, 2 * h, 2 * w, cs, generator=g).to(dev).to(torch.bfloat16)
+            wt = (torch.randn(cout, cx + cs, 3, 3, generator=g) / ((cx + cs) * 9) ** 0.5).to(dev)
+            bias = torch.randn(cout, generator=g).to(dev)
+            out = ops.conv2d_upcat_subpixel(x, skip, packing.pack_upcat_subpixel(wt, cx), bias.repeat(4).contiguous(), relu=relu)
+            torch.cuda.synchronize()
+            xi = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+            ref = F.conv2d(torch.cat([xi, skip.float().permute(0, 3, 1, 2)], 1), wt.to(torch.bfloat16).float(), bias, padding=1)
+            ref = (ref.relu() if relu else ref).permute(0, 2, 3, 1)
+            err = (out.float() - ref).abs()
+            bad = (err > 1.5e-2 * ref.abs().clamp_min(1.0)).float().mean().item()
+            print(f"{'OK  ' if bad == 0 else 'FAIL'} spx   {name:<24s} max_err={err.max().item():.4g} ref_max={ref.abs().max().item():.4g} bad_frac={bad:.4g}", flush=True)
+            nfail += (bad != 0)
+        except Exception as ex:  # noqa: BLE001
+            nfail += 1
+            print(f"EXC  spx {case[0]}: {ex}", flush=True)
             traceback.print_exc()
             if "CUDA" in str(ex) or "fault" in str(ex):
                 print("aborting after CUDA error")

@@ -27,14 +27,17 @@ def main():
         ho, wo = (2 * h, 2 * w) if up else (h, w)
         skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
         cin = cx + cs
-        wp = packing.pack_taps(torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5)
-        b = torch.zeros(cout, device=dev)
+        wt = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+        wp = packing.pack_upcat_subpixel(wt, cx) if up == "spx" else packing.pack_taps(wt)
+        b = torch.zeros(4 * cout if up == "spx" else cout, device=dev)
         out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
         res = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16) if args.residual else None
 
         def run():
             if res is not None and not up and skip is None:
                 ops.conv2d(x, wp, b, 3, 3, 1, 1, relu=True, residual=res, out=out)
+            elif up == "spx":
+                ops.conv2d_upcat_subpixel(x, skip, wp, b, relu=True, out=out)
             else:
                 ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
         for _ in range(3):

@@ -19,6 +19,7 @@ IN_U8_NHWC = 1
 PACK_TAPS = 0
 PACK_STEM_S2D = 1
 PACK_UP2X_SHUFFLE = 2
+PACK_UPCAT_SUBPIXEL = 3
 
 
 class LayerDesc(C.Structure):
@@ -30,6 +31,7 @@ class LayerDesc(C.Structure):
         ("pack", C.c_int32), ("relu", C.c_int32), ("has_residual", C.c_int32),
         ("w_elems", C.c_int64), ("b_elems", C.c_int64),
         ("flops_per_image", C.c_double),
+        ("cin_skip", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -48,6 +50,8 @@ SIGNATURES = {
                                              C.c_int, _P]),
     "uwm_conv2d_up2x_shuffle_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                                     C.c_int, _P, C.c_int, _P]),
+    "uwm_conv2d_upcat_subpixel_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int,
+                                                      C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "uwm_head_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,
                                      _P, C.c_float, _P]),
     "uwm_maxpool3x3s2_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),

@@ -101,6 +101,7 @@ struct HaloKArgs {
   float* logits;
   uint8_t* mask;
   float thr_logit;
+  int spx_cpp, spx_slices;                  // SPX kernels: 64-channel chunks per parity plane of src[1]; weight slices per tile
   int mix;                                  // !A_TMA kernels: chunks of src[1] arrive as TMA boxes (swizzled stage layout)
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
   int shuffle;                              // > 0: sub-pixel mode, real cout; GEMM column n = parity*shuffle + co is stored to
@@ -151,6 +152,18 @@ __device__ __forceinline__ void halo_trace(const HaloKArgs& p, int slot) {
   if (p.trace && blockIdx.x == 0 && slot < 600) p.trace[slot] = clock64();
 }
 
+// dbg bit 8 (with a trace buffer of >= 1024 + 4*grid slots): every CTA stamps its start and exit in nanoseconds
+// and in SM cycles,
+// so consecutive launches show the gap between one grid's last exit and the next grid's first tile
+__device__ __forceinline__ void halo_trace_cta(const HaloKArgs& p, int which) {
+  if (p.trace && (p.dbg & 8)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[1024 + 4 * blockIdx.x + which] = (long long)t;
+    p.trace[1024 + 4 * blockIdx.x + 2 + which] = clock64();
+  }
+}
+
 struct HaloTile { int n_tile, w0, h0, img; };
 template <int TG>
 __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
@@ -164,7 +177,14 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
   return t;
 }
 
-template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA>
+// SPX (sub-pixel conv with a skip source): conv3x3(concat(nearest-2x(x), skip)) computed on x's grid with one GEMM
+// column group per output parity (the epilogue's pixel shuffle scatters them).  x chunks are ordinary 3x3 chunks with
+// pre-summed weights; the skip source, stored at the OUTPUT resolution, arrives as four parity planes (TMA boxes with
+// element stride 2) of 64-channel chunks, and plane (ph,pw) only meets the 2x2 taps {1-ph,2-ph} x {1-pw,2-pw} of the
+// 3x3 block neighbourhood: 16 (plane, tap) pairs instead of the 36 a dense 3x3 conv over the space-to-depth input
+// would issue.  Weight slices stream in issue order (p.spx_slices per tile, one per stage); in SPX kernels tm_out and
+// tm_res are the weight maps with half- and quarter-height boxes (the epilogue stores without TMA).
+template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, bool SPX = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -216,7 +236,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();
-  if (threadIdx.x == 0) halo_trace(p, 0);
+  if (threadIdx.x == 0) { halo_trace(p, 0); halo_trace_cta(p, 0); }
   for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += kHaloThreads) s_bias[i] = __ldg(p.bias + i);
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), A_TMA ? 1 : kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
@@ -226,7 +246,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     for (int w = 0; w < 8; ++w) mbar_init(resbar(w), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
-    if (p.ep_tma) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
+    if (p.ep_tma || SPX) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
     if (A_TMA) { tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); }
     else if (p.mix) tma_prefetch_desc(&tm_a1);
   }
@@ -261,6 +281,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
         const int ncol = (tile - fast_div(tile, p.div_ntiles) * p.n_tiles) * p.block_n;
+        if (SPX) {
+          // slices in the MMA warp's issue order; each carries only the rows (GEMM columns) its tap can reach
+          // (see spx_tap): all bn, half of them or a quarter, through the map with the matching box height
+          int sl = 0, par = 0, cc = 0;       // no divisions here: this one thread feeds ~25 slices per tile
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            const bool is_x = ch < p.split_chunk;
+            const int nt = is_x ? 9 : 4;
+            for (int t = 0; t < nt; ++t, ++sl) {
+              if (leader) {
+                int R, C;
+                if (is_x) {
+                  const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);                 // (1,1) first, then row-major
+                  R = (tap >= 6) ? 2 : (tap >= 3 ? 1 : 0); C = tap - 3 * R;
+                } else {
+                  R = 1 - (par >> 1) + (t >> 1); C = 1 - (par & 1) + (t & 1);
+                }
+                const int qn = (R == 1) ? 4 : (C == 1 ? 2 : 1);
+                const int qoff = (R == 1) ? 0 : 2 * (R == 2) + (C == 1 ? 0 : (C == 2));
+                const CUtensorMap* tm = (qn == 4) ? &tm_wgt : (qn == 2 ? &tm_out : &tm_res);
+                mbar_wait(bempty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)(qn * (p.block_n >> 2)) * KC * 2u);
+                tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, tm, bfull_bar(s), sl * KC, qoff * (p.block_n >> 2));
+              }
+              if (++s == p.b_stages) { s = 0; ph ^= 1u; }
+            }
+            if (!is_x && ++cc == p.spx_cpp) { cc = 0; ++par; }
+          }
+          continue;
+        }
         for (int ch = 0; ch < p.chunks; ++ch) {
           for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
             if (leader) {
@@ -293,6 +342,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const uint32_t b_stage_units = b_stage_bytes >> 4;
     const uint32_t bn = (uint32_t)p.block_n;
     const bool skip_mma = p.dbg & 2;
+    const uint32_t idesc_half = make_idesc_bf16(kTileM, SPX ? p.block_n >> 1 : p.block_n);
+    const uint32_t idesc_quarter = make_idesc_bf16(kTileM, SPX ? p.block_n >> 2 : p.block_n);
     if (elect_one()) {
       if (RESIDENT) mbar_wait(bres_bar, 0);
       int sa = 0; uint32_t pha = 0;
@@ -312,15 +363,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           uint32_t b_lo = b_lo0 + (uint32_t)(ch * NT) * b_slice_units;   // resident: slice (ch, tap 0)
           int j = 0;                                                      // streamed: slice inside the stage
           // one K chunk: all taps x sub-tiles x K=16 slices, instantiated per stage layout (immediate offsets)
-          auto issue_chunk = [&](auto swz_c) {
+          auto issue_chunk = [&](auto swz_c, auto r0_c, auto c0_c, auto nr_c, auto nc_c) {
             constexpr bool SWZ = decltype(swz_c)::value;
+            constexpr int R0 = decltype(r0_c)::value, C0 = decltype(c0_c)::value;     // tap sub-rectangle of the halo
+            constexpr int NR = decltype(nr_c)::value, NC = decltype(nc_c)::value;
             constexpr uint32_t a_hi = SWZ ? a_hi_sw : a_hi_pl;
             constexpr uint32_t a_px_units = SWZ ? (ROWB >> 4) : 1u;       // 16-byte units per halo pixel step
             constexpr uint32_t a_k_units = SWZ ? 2u : 2u * PLANE_UNITS;   // 16-byte units per K=16 slice
             const uint32_t a_st = (SWZ ? a_lo0_sw : a_lo0_pl) + (uint32_t)sa * a_stage_units;
 #pragma unroll
-            for (int tap = 0; tap < NT; ++tap) {
-              const uint32_t shift = (uint32_t)((tap / KW) * PW + (tap % KW));
+            for (int tap = 0; tap < NR * NC; ++tap) {
+              const uint32_t shift = (uint32_t)((R0 + tap / NC) * PW + (C0 + tap % NC));
               if (!RESIDENT && j == 0) {
                 mbar_wait_fast(bfull_bar(sb), phb);
                 tc_fence_after();
@@ -346,12 +399,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               }
             }
           };
+          using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+          using I2 = std::integral_constant<int, 2>;
+          using IH = std::integral_constant<int, KH>; using IW = std::integral_constant<int, KW>;
           if (!skip_mma) {
-            if (A_TMA) issue_chunk(std::true_type{});
-            else if (p.mix && ch >= p.split_chunk) issue_chunk(std::true_type{});    // skip source: TMA box
-            else issue_chunk(std::false_type{});                                     // upsampled source: gather
+            if (SPX) {
+              // One tap (R,C) of the 3x3 block neighbourhood.  Row R = 0 only reaches output parity qh = 0, R = 2 only
+              // qh = 1, R = 1 both (same for columns), so with GEMM columns ordered (qh, qw, co) the tap needs
+              // N = bn (R == 1), bn/2 at column qh*bn/2 (R != 1, C == 1) or bn/4 at column (2qh+qw)*bn/4: fewer
+              // tensor cycles (32 + N/4 per MMA) and a smaller weight slice.  The first tap of a tile is (1,1): it
+              // writes all bn columns, everything after it accumulates.
+              auto spx_tap = [&](auto r_c, auto c_c, uint32_t accumulate) {
+                constexpr int R = decltype(r_c)::value, C = decltype(c_c)::value;
+                constexpr int QN = (R == 1) ? 4 : (C == 1 ? 2 : 1);
+                constexpr int QOFF = (R == 1) ? 0 : 2 * (R == 2) + (C == 1 ? 0 : (C == 2));
+                constexpr uint32_t shift = (uint32_t)(R * PW + C);
+                const uint32_t a_st = a_lo0_sw + (uint32_t)sa * a_stage_units;
+                const uint32_t idesc_t = QN == 4 ? idesc : (QN == 2 ? idesc_half : idesc_quarter);
+                mbar_wait_fast(bfull_bar(sb), phb);
+                tc_fence_after();
+                const uint32_t b_st = b_lo0 + (uint32_t)sb * b_stage_units;
+#pragma unroll
+                for (int g = 0; g < TG; ++g) {
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    const uint32_t d = tmem_acc + g * bn + QOFF * (bn >> 2);
+                    if (k == 0) umma_halo<false>(d, a_st + (shift + 8u * g) * (ROWB >> 4) + 2u * k, a_hi_sw, b_st + 2u * k, b_hi, idesc_t, accumulate);
+                    else umma_halo<true>(d, a_st + (shift + 8u * g) * (ROWB >> 4) + 2u * k, a_hi_sw, b_st + 2u * k, b_hi, idesc_t, 1u);
+                  }
+                }
+                umma_commit(bempty_bar(sb));
+                if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
+              };
+              if (ch < p.split_chunk) {
+                spx_tap(I1{}, I1{}, (uint32_t)ch);
+                spx_tap(I0{}, I0{}, 1u); spx_tap(I0{}, I1{}, 1u); spx_tap(I0{}, I2{}, 1u);
+                spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I2{}, 1u);
+                spx_tap(I2{}, I0{}, 1u); spx_tap(I2{}, I1{}, 1u); spx_tap(I2{}, I2{}, 1u);
+              } else {
+                // parity plane (ph,pw) of the skip source: taps {1-ph, 2-ph} x {1-pw, 2-pw}
+                const int par = (ch - p.split_chunk) / p.spx_cpp;
+                if (par == 0) { spx_tap(I1{}, I1{}, 1u); spx_tap(I1{}, I2{}, 1u); spx_tap(I2{}, I1{}, 1u); spx_tap(I2{}, I2{}, 1u); }
+                else if (par == 1) { spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I1{}, 1u); spx_tap(I2{}, I0{}, 1u); spx_tap(I2{}, I1{}, 1u); }
+                else if (par == 2) { spx_tap(I0{}, I1{}, 1u); spx_tap(I0{}, I2{}, 1u); spx_tap(I1{}, I1{}, 1u); spx_tap(I1{}, I2{}, 1u); }
+                else { spx_tap(I0{}, I0{}, 1u); spx_tap(I0{}, I1{}, 1u); spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I1{}, 1u); }
+              }
+            }
+            else if (A_TMA) issue_chunk(std::true_type{}, I0{}, I0{}, IH{}, IW{});
+            else if (p.mix && ch >= p.split_chunk) issue_chunk(std::true_type{}, I0{}, I0{}, IH{}, IW{});  // skip source: TMA box
+            else issue_chunk(std::false_type{}, I0{}, I0{}, IH{}, IW{});                                   // upsampled source: gather
           } else if (!RESIDENT) {
-            for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
+            for (int tap0 = 0; tap0 < ((SPX && ch >= p.split_chunk) ? 4 : NT); tap0 += p.kpb) {
               mbar_wait_fast(bfull_bar(sb), phb);
               umma_commit(bempty_bar(sb));
               if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
@@ -577,7 +675,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
               if (ch < p.split_chunk)
                 tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase, hbase, t.img);
-              else
+              else if (SPX) {
+                // parity plane (ph,pw) of the full-resolution skip source: halo block b is pixel 2b + parity
+                const int e = ch - p.split_chunk, par = e / p.spx_cpp, cc = e - par * p.spx_cpp;
+                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), cc * KC, 2 * wbase + (par & 1),
+                            2 * hbase + (par >> 1), t.img);
+              } else
                 tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), (ch - p.split_chunk) * KC, wbase,
                             hbase, t.img);
             } else {
@@ -641,6 +744,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) halo_trace_cta(p, 1);
 }
 
 }  // namespace uwm

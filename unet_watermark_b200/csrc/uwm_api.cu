@@ -148,7 +148,7 @@ struct ConvSpec {
 
 struct ConvLaunch {
   int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
-  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0;   // halo: template instantiation
+  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0, spx = 0;   // halo: template instantiation
   CUtensorMap tm_act, tm_wgt, tm_out, tm_res, tm_a0, tm_a1;
   ConvKArgs args;
   HaloKArgs hargs;
@@ -193,8 +193,123 @@ static bool halo_enabled() {
   return v == 1;
 }
 
+// Sub-pixel form of the decoder's conv1 WITH a skip (conv_halo.cuh, SPX): conv3x3(concat(up2x(x), skip)) on x's grid.
+//   s.h, s.w : x's (low) resolution; skip and out are [n, 2h, 2w, .]; s.shuffle = real cout, s.cout_pad = 4*cout
+//   weights  : UWM_PACK_UPCAT_SUBPIXEL, [4*cout][9*cin/64 + 16*cin2/64 slices][64] in issue order
+// Tensor-pipe cycles per 128 source pixels (= 512 outputs), cin = cin2 = 64, cout = 32: (9 + 16) x 4 MMAs of N = 128
+// = 6400, against 4 x 72 MMAs of N = 32 = 11 800 for the gathered conv at the output resolution.
+static int build_halo_spx(const ConvSpec& s, ConvLaunch* L) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const int kc = 64, bn = s.cout_pad;
+  if (s.cin % kc || s.cin2 % kc || !s.cin || !s.cin2)
+    return fail(UWM_EINVAL, "sub-pixel upcat conv: cin=%d+%d: each must be a non-zero multiple of 64", s.cin, s.cin2);
+  if (s.shuffle % 16 || bn != 4 * s.shuffle || bn > 256)
+    return fail(UWM_EINVAL, "sub-pixel upcat conv: cout=%d must be a multiple of 16, <= 64", s.shuffle);
+  if ((s.x_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.x) & 15) || (s.x2_pitch * 2) % 16 ||
+      (reinterpret_cast<uintptr_t>(s.x2) & 15) || (s.out_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.out) & 15))
+    return fail(UWM_EINVAL, "sub-pixel upcat conv: activation/output base and pitch must be 16-byte aligned");
+  if (s.res || s.head) return fail(UWM_EINVAL, "sub-pixel upcat conv: no residual / head epilogue");
+  L->halo = 1;
+  HaloKArgs& a = L->hargs;
+  memset(&a, 0, sizeof(a));
+  const int tg = (bn <= 128 && s.w >= 2 * kHaloTW) ? 2 : 1;          // two accumulator sets of tg*bn columns
+  L->kh = 3; L->kw = 3; L->kc = kc; L->tg = tg; L->resident = 0; L->a_tma = 1; L->spx = 1;
+  a.n_img = s.n; a.h = s.h; a.w = s.w;
+  a.chunks = s.cin / kc + 4 * (s.cin2 / kc);
+  a.split_chunk = s.cin / kc;
+  a.spx_cpp = s.cin2 / kc;
+  a.spx_slices = 9 * (s.cin / kc) + 16 * (s.cin2 / kc);
+  a.dh_min = -1; a.dw_min = -1;
+  a.cin_total = s.cin + s.cin2;
+  a.tiles_w = (s.w + kHaloTW * tg - 1) / (kHaloTW * tg);
+  a.tiles_h = (s.h + kHaloTH - 1) / kHaloTH;
+  a.block_n = bn; a.n_tiles = 1; a.cout = bn;
+  a.total_tiles = a.tiles_w * a.tiles_h * s.n;
+  a.div_ntiles = make_fastdiv(1);
+  a.div_tw = make_fastdiv(a.tiles_w);
+  a.div_th = make_fastdiv(a.tiles_h);
+  a.pw_magic = 65536u / (uint32_t)halo_pw(tg, 3) + 1u;
+  const unsigned grid = (unsigned)std::min(a.total_tiles, num_sms());
+  a.b_slice_bytes = (uint32_t)bn * kc * 2u;                           // >= 8 KB, 1024-aligned
+  a.kpb = 1;
+  const size_t a_stage_bytes = (((size_t)halo_npix(tg, 3, 3) * kc * 2) + 1023) & ~(size_t)1023;
+  const size_t kBudget = 206u * 1024u;
+  // an activation stage lasts 4 or 9 taps (2000-4600 tensor cycles): two are enough.  The weight ring gets the rest:
+  // slices are consumed every ~512 cycles and must cover the L2 latency under load (~3000 cycles)
+  a.a_stages = 2;
+  { const char* e = getenv("UWM_SPX_ASTAGES"); if (e && atoi(e) >= 2 && atoi(e) <= 4) a.a_stages = atoi(e); }
+  a.b_stages = (int)std::min<size_t>(12, (kBudget - a.a_stages * a_stage_bytes) / a.b_slice_bytes);
+  if (a.b_stages < 2) return fail(UWM_ESTATE, "sub-pixel upcat conv: rings do not fit shared memory");
+  a.nacc_log2 = 1;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * tg * bn)) cols <<= 1;
+  a.tmem_cols = cols;
+  a.bias = s.bias;
+  a.out = static_cast<__nv_bfloat16*>(s.out);
+  a.out_pitch = s.out_pitch;
+  a.relu = s.relu;
+  a.shuffle = s.shuffle;
+  a.ep_tma = 0; a.ep_cols = 16;
+  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.trace = g_halo_trace;
+  a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x); a.src[0].pitch = s.x_pitch; a.src[0].h = s.h; a.src[0].w = s.w;
+  a.src[1].ptr = static_cast<const __nv_bfloat16*>(s.x2); a.src[1].pitch = s.x2_pitch; a.src[1].h = 2 * s.h; a.src[1].w = 2 * s.w;
+  { const char* e = getenv("UWM_VERBOSE");
+    if (e && e[0] == '1')
+      fprintf(stderr, "halo conv (sub-pixel upcat) %dx%dx%d cin=%d+%d cout=4x%d: bn=%d tg=%d tiles=%d grid=%u a_stages=%d b_stages=%d slices=%d\n",
+              s.n, s.h, s.w, s.cin, s.cin2, s.shuffle, bn, tg, a.total_tiles, grid, a.a_stages, a.b_stages, a.spx_slices); }
+  L->grid = grid;
+  L->smem = 1024 + (size_t)a.b_stages * a.b_slice_bytes + (size_t)a.a_stages * a_stage_bytes + 1024 + (size_t)bn * 4;
+
+  const cuuint64_t ktot = (cuuint64_t)a.spx_slices * kc;
+  cuuint64_t dims[2] = {ktot, (cuuint64_t)bn};
+  cuuint64_t strides[1] = {ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = enc(&L->tm_wgt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims, strides, box, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(sub-pixel wgt) -> %d", (int)r);
+  // taps that reach one output row parity / one output parity only load that half / quarter of the rows:
+  // the kernel takes those two maps in the (otherwise unused) output and residual map slots
+  for (int q = 2; q <= 4; q <<= 1) {
+    cuuint32_t qbox[2] = {(cuuint32_t)kc, (cuuint32_t)(bn / q)};
+    r = enc(q == 2 ? &L->tm_out : &L->tm_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims, strides,
+            qbox, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(sub-pixel wgt, 1/%d rows) -> %d", q, (int)r);
+  }
+  const cuuint32_t pw = (cuuint32_t)halo_pw(tg, 3), ph = (cuuint32_t)(kHaloTH + 2);
+  {   // x at its own resolution: the ordinary halo box
+    cuuint64_t adims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
+    cuuint64_t astr[3] = {(cuuint64_t)s.x_pitch * 2, (cuuint64_t)s.w * s.x_pitch * 2, (cuuint64_t)s.h * s.w * s.x_pitch * 2};
+    cuuint32_t abox[4] = {(cuuint32_t)kc, pw, ph, 1};
+    cuuint32_t aest[4] = {1, 1, 1, 1};
+    r = enc(&L->tm_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.x), adims, astr, abox, aest,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(sub-pixel x) -> %d", (int)r);
+  }
+  {   // skip at twice the resolution, every second pixel of every second row: one parity plane per box
+    cuuint64_t adims[4] = {(cuuint64_t)s.cin2, (cuuint64_t)2 * s.w, (cuuint64_t)2 * s.h, (cuuint64_t)s.n};
+    cuuint64_t astr[3] = {(cuuint64_t)s.x2_pitch * 2, (cuuint64_t)2 * s.w * s.x2_pitch * 2,
+                          (cuuint64_t)4 * s.h * s.w * s.x2_pitch * 2};
+    cuuint32_t abox[4] = {(cuuint32_t)kc, 2 * pw, 2 * ph, 1};
+    cuuint32_t aest[4] = {1, 2, 2, 1};
+    r = enc(&L->tm_a1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.x2), adims, astr, abox, aest,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(sub-pixel skip, element stride 2) -> %d (box %u,%u,%u)", (int)r, abox[0],
+                  abox[1], abox[2]);
+  }
+  return UWM_OK;
+}
+
 // Halo-resident kernel (conv_halo.cuh): stride-1 convs, optional fused upsample + concat.
 static int build_halo(const ConvSpec& s, ConvLaunch* L) {
+  if (s.shuffle && s.x2) return build_halo_spx(s, L);
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (s.stride != 1) return fail(UWM_EINVAL, "halo conv: stride %d unsupported", s.stride);
@@ -566,7 +681,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   if (!L) {                                                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES, AT>,                                    \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                    \
-  } else if (L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES &&           \
+  } else if (!L->spx && L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES && \
              (L->a_tma != 0) == AT) {                                                                           \
     launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
                L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                                                   \
@@ -585,6 +700,18 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   UWM_HALO_CASE1(64, 1, 1, 1, false, true) UWM_HALO_CASE1(64, 1, 1, 2, false, true)
 #undef UWM_HALO_CASE
 #undef UWM_HALO_CASE1
+  // sub-pixel upcat conv (SPX): 64-channel chunks, streamed weights, TMA-fed
+#define UWM_HALO_SPX(TG)                                                                                          \
+  if (!L) {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, false, true, true>,                              \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
+  } else if (L->spx && L->tg == TG) {                                                                             \
+    launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, true>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,  \
+               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
+    return UWM_OK;                                                                                                \
+  }
+  UWM_HALO_SPX(1) UWM_HALO_SPX(2)
+#undef UWM_HALO_SPX
   if (!L) return UWM_OK;
   return fail(UWM_ESTATE, "halo conv: no kernel instantiated for kc=%d %dx%d tg=%d resident=%d a_tma=%d", L->kc, L->kh,
               L->kw, L->tg, L->resident, L->a_tma);
@@ -689,6 +816,25 @@ extern "C" int uwm_conv2d_up2x_shuffle_nhwc_bf16(const void* d_x, int n, int h, 
   s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
   ConvLaunch L;
   int rc = build_halo(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uwm_conv2d_upcat_subpixel_nhwc_bf16(const void* d_x, int n, int h, int w, int c_x, int x_pitch,
+                                                   const void* d_skip, int c_skip, int skip_pitch, const void* d_wgt,
+                                                   const float* d_bias, int cout, int relu, void* d_y, int y_pitch,
+                                                   void* stream) {
+  if (!d_x || !d_skip || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_upcat_subpixel: null pointer");
+  if (cout % 16 || 4 * cout > 256) return fail(UWM_EINVAL, "conv2d_upcat_subpixel: cout=%d must be a multiple of 16, <= 64", cout);
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = c_x; s.x_pitch = x_pitch;
+  s.x2 = d_skip; s.cin2 = c_skip; s.x2_pitch = skip_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = 4 * cout; s.cout_pad = 4 * cout; s.shuffle = cout;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 1; s.h_out = h; s.w_out = w;
+  s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_halo_spx(s, &L);
   if (rc) return rc;
   return launch_conv(L, static_cast<cudaStream_t>(stream));
 }
@@ -844,7 +990,7 @@ struct uwm_model {
 
 static int add_layer(uwm_model* m, const std::string& conv_key, const std::string& bn_key, int cin,
                      int cout, int k, int stride, int pad, int relu, int has_res, bool stem = false,
-                     bool shuffle = false) {
+                     bool shuffle = false, int spx_cskip = 0) {
   Layer L;
   memset(&L.d, 0, sizeof(L.d));
   snprintf(L.d.conv_key, sizeof(L.d.conv_key), "%s", conv_key.c_str());
@@ -856,6 +1002,13 @@ static int add_layer(uwm_model* m, const std::string& conv_key, const std::strin
   if (stem) {
     L.d.pack = UWM_PACK_STEM_S2D;
     L.d.w_elems = (int64_t)L.d.cout_pad * 16 * 16;
+  } else if (shuffle && spx_cskip > 0) {
+    // decoder conv1 WITH a skip, sub-pixel form: see build_halo_spx
+    L.shuffle = true;
+    L.d.pack = UWM_PACK_UPCAT_SUBPIXEL;
+    L.d.cin_skip = spx_cskip;
+    L.d.cout_pad = 4 * cout;
+    L.d.w_elems = (int64_t)L.d.cout_pad * 64 * (9 * ((cin - spx_cskip) / 64) + 16 * (spx_cskip / 64));
   } else if (shuffle) {
     // conv3x3 over a nearest-2x upsampled input == 3x3 conv on the SOURCE grid producing 4*cout channels (one group
     // per output parity, weights pre-summed over the taps that hit the same source pixel) + pixel shuffle
@@ -985,8 +1138,14 @@ static int build_plan(uwm_model* m) {
     const int bh = H >> (4 - i), bw = W >> (4 - i);
     const std::string pre = fmt("decoder.blocks.%d", i);
     TRef t1 = m->dense(bh, bw, dec[i]);
-    const bool subpixel = (cs[i] == 0) && subpixel_enabled() && 4 * dec[i] <= 256;
-    int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0, false, subpixel);
+    // sub-pixel forms (N = 4*cout <= 256 on the source grid): without a skip, and with a skip when both sources
+    // split into 64-channel chunks (build_halo_spx)
+    static const bool spx_on = []{ const char* e = getenv("UWM_SPX"); return !(e && e[0] == '0'); }();
+    const bool spx = cs[i] > 0 && spx_on && subpixel_enabled() && 4 * dec[i] <= 256 && dec[i] % 16 == 0 &&
+                     cx[i] % 64 == 0 && cs[i] % 64 == 0;
+    const bool subpixel = ((cs[i] == 0) && subpixel_enabled() && 4 * dec[i] <= 256) || spx;
+    int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0, false, subpixel,
+                       spx ? cs[i] : 0);
     add_conv(m, l1, x, t1, nullptr, false, /*up=*/true, cs[i] ? &skip[i] : nullptr);
     TRef t2 = m->dense(bh, bw, dec[i]);
     int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0);

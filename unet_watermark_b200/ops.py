@@ -91,6 +91,25 @@ def conv2d_up2x_shuffle(x: torch.Tensor, w_shuffle: torch.Tensor, bias4: torch.T
     return out
 
 
+def conv2d_upcat_subpixel(x: torch.Tensor, skip: torch.Tensor, w_spx: torch.Tensor, bias4: torch.Tensor,
+                          relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv3x3(concat(nearest_up2x(x), skip)) (+bias)(+ReLU) as a sub-pixel conv on x's grid.
+    x: [N,h,w,Cx]; skip: [N,2h,2w,Cs]; w_spx: packing.pack_upcat_subpixel(w, Cx); bias4: bias repeated 4x (fp32)."""
+    _require_cuda(x, skip, w_spx, bias4, out)
+    lib = _lib.load()
+    n, h, w, cx = x.shape
+    if skip.shape[0] != n or skip.shape[1] != 2 * h or skip.shape[2] != 2 * w:
+        raise ValueError(f"skip {tuple(skip.shape)} must be [N, 2h, 2w, Cs] for x {tuple(x.shape)}")
+    cout = w_spx.shape[0] // 4
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_upcat_subpixel_nhwc_bf16(x.data_ptr(), n, h, w, cx, _pitch(x), skip.data_ptr(), skip.shape[3],
+                                                 _pitch(skip), w_spx.data_ptr(), bias4.data_ptr(), cout, int(relu),
+                                                 out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_upcat_subpixel_nhwc_bf16")
+    return out
+
+
 def head(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, threshold: Optional[float] = 0.5,
          thr_on_logits: bool = False, want_logits: bool = True, apply_sigmoid: bool = False):
     """conv3x3(Cin->1)+bias -> (fp32 logits [N,H,W] or None, uint8 mask [N,H,W] or None)."""

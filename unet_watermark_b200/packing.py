@@ -48,12 +48,12 @@ def pack_stem_s2d(w: torch.Tensor, cout_pad: int | None = None) -> torch.Tensor:
     return out.reshape(cout_pad, 256).to(torch.bfloat16).contiguous()
 
 
-def pack_up2x_shuffle(w: torch.Tensor) -> torch.Tensor:
+def pack_up2x_shuffle_f32(w: torch.Tensor) -> torch.Tensor:
     """3x3 conv applied to a nearest-2x upsampled input, as a 3x3 conv on the source grid with 4*Cout outputs.
 
     Output pixel (2i+ph, 2j+pw) reads upsampled pixels (2i+ph+dy, 2j+pw+dx), dy,dx in {-1,0,1}, i.e. source pixels
     (i + floor((ph+dy)/2), j + floor((pw+dx)/2)): taps that land on the same source pixel are summed (fp32) and the
-    sum is rounded once to bf16.  Returns bf16 [4*Cout, 9*Cin]; row (ph*2+pw)*Cout + co, K index (a*3+b)*Cin + c for
+    sum is rounded once to bf16 by the caller.  Returns fp32 [4*Cout, 9*Cin]; row (ph*2+pw)*Cout + co, K index (a*3+b)*Cin + c for
     source offset (a-1, b-1).  The kernel's epilogue scatters group (ph,pw) to pixel (2i+ph, 2j+pw)."""
     cout, cin, kh, kw = w.shape
     assert (kh, kw) == (3, 3), "sub-pixel packing expects a 3x3 kernel"
@@ -66,7 +66,54 @@ def pack_up2x_shuffle(w: torch.Tensor) -> torch.Tensor:
                 for dx in (-1, 0, 1):
                     b = (pw + dx) // 2
                     out[ph, pw, :, a + 1, b + 1, :] += wf[:, :, dy + 1, dx + 1]
-    return out.reshape(4 * cout, 9 * cin).to(torch.bfloat16).contiguous()
+    return out.reshape(4 * cout, 9 * cin)
+
+
+def pack_up2x_shuffle(w: torch.Tensor) -> torch.Tensor:
+    """bf16 [4*Cout, 9*Cin] sub-pixel weights of a 3x3 conv over a nearest-2x upsampled input (see above)."""
+    return pack_up2x_shuffle_f32(w).to(torch.bfloat16).contiguous()
+
+
+# x taps of the sub-pixel upcat conv in issue order: the centre tap first (it reaches every output parity, so the
+# tile's first MMA writes all GEMM columns), then row-major
+SPX_X_TAP_ORDER = (4, 0, 1, 2, 3, 5, 6, 7, 8)
+
+
+def pack_upcat_subpixel(w: torch.Tensor, c_x: int) -> torch.Tensor:
+    """conv3x3 over concat(nearest-2x(x), skip) as a sub-pixel conv on x's grid (UWM_PACK_UPCAT_SUBPIXEL).
+
+    w: [Cout, c_x + c_skip, 3, 3].  Output pixel (2i+qh, 2j+qw) is GEMM row (i,j), column (qh*2+qw)*Cout + co.
+    K is a sequence of 64-channel slices in the order the kernel issues them:
+      * per 64-channel chunk of x: the 9 taps of pack_up2x_shuffle (taps of the upsampled conv that land on the same
+        source pixel summed in fp32, rounded once), centre tap first (SPX_X_TAP_ORDER);
+      * per parity plane (ph,pw) of skip, per 64-channel chunk: taps r in {1-ph, 2-ph}, c in {1-pw, 2-pw} of the 3x3
+        block neighbourhood.  Block offset r-1 of plane ph is skip row 2(i+r-1)+ph, which output row 2i+qh reads
+        with kernel row 2(r-1)+ph-qh+1 - a zero slice entry when that is outside 0..2.
+    Returns bf16 [4*Cout, 64 * (9*c_x/64 + 16*c_skip/64)]."""
+    cout, cin, kh, kw = w.shape
+    c_s = cin - c_x
+    assert (kh, kw) == (3, 3) and c_x % 64 == 0 and c_s % 64 == 0 and c_x > 0 and c_s > 0
+    wf = w.detach().float()
+    slices = []
+    wx = pack_up2x_shuffle_f32(wf[:, :c_x]).reshape(4 * cout, 9, c_x)
+    for ch in range(c_x // 64):
+        for tap in SPX_X_TAP_ORDER:
+            slices.append(wx[:, tap, ch * 64:(ch + 1) * 64])
+    for ph in range(2):
+        for pw in range(2):
+            for cc in range(c_s // 64):
+                wsk = wf[:, c_x + cc * 64: c_x + (cc + 1) * 64]              # [cout, 64, 3, 3]
+                for r in (1 - ph, 2 - ph):
+                    for c in (1 - pw, 2 - pw):
+                        sl = torch.zeros(2, 2, cout, 64, dtype=torch.float32, device=w.device)
+                        for qh in range(2):
+                            kr = 2 * (r - 1) + ph - qh + 1
+                            for qw in range(2):
+                                kcol = 2 * (c - 1) + pw - qw + 1
+                                if 0 <= kr <= 2 and 0 <= kcol <= 2:
+                                    sl[qh, qw] = wsk[:, :, kr, kcol]
+                        slices.append(sl.reshape(4 * cout, 64))
+    return torch.cat(slices, dim=1).to(torch.bfloat16).contiguous()
 
 
 def pad_bias(b: torch.Tensor, cout_pad: int) -> torch.Tensor:
