@@ -55,6 +55,12 @@ extern "C" {
                                  3x3 kernel); bias = 4 copies (packing.pack_upcat_subpixel).  Tap row 0 / 2 of the
                                  block neighbourhood only reaches qh = 0 / 1 (same for columns): the kernel loads
                                  and multiplies only those rows of such a slice                                   */
+#define UWM_PACK_S2D_CONV 4    /* conv3x3 on a [.,2h,2w,cin] tensor stored space-to-depth [.,h,w,4*cin] (channel =
+                                 (ph*2+pw)*cin + ci), producing the same layout: [4*cout][3*3][4*cin] bf16 in
+                                 UWM_PACK_TAPS order over BLOCKS, row (qh*2+qw)*cout + co, entry = w[co, ci,
+                                 2(r-1)+ph-qh+1, 2(c-1)+pw-qw+1] for block tap (r,c), zero outside the 3x3 kernel;
+                                 bias = 4 copies.  The 1-channel head: rows 0..3 = the 4 output parities, padded
+                                 to 16 rows (packing.pack_s2d_conv3x3)                                           */
 #define UWM_PACK_STEM_S2D 1   /* 7x7/s2 stem as 4x4/s1 over the 2x2 space-to-depth input:
                                  [64][4*4][16] bf16, channel = (ph*2+pw)*3 + c, 12..15 zero      */
 
@@ -116,6 +122,20 @@ int uwm_conv2d_upcat_subpixel_nhwc_bf16(const void* d_x, int n, int h, int w, in
                                         const void* d_skip, int c_skip, int skip_pitch, const void* d_wgt,
                                         const float* d_bias, int cout, int relu, void* d_y, int y_pitch,
                                         void* stream);
+
+/* conv3x3 'same' (+bias)(+ReLU) on a 16-channel tensor kept space-to-depth: x, y = [n,h,w,4*16] standing for
+ * [n,2h,2w,16] (channel = (ph*2+pw)*16 + c, what uwm_conv2d_nhwc_bf16 with UWM_PACK_UP2X_SHUFFLE weights writes).
+ * wgt: UWM_PACK_S2D_CONV [64][9*64].  Parity plane (ph,pw) can only meet block taps {1-ph,2-ph} x {1-pw,2-pw}: 16 of
+ * the 36 (tap, plane) MMAs are issued, each with N = 64 instead of 16.  Same arithmetic as the conv at full
+ * resolution (every product of the reference conv appears exactly once; fp32 accumulation order differs). */
+int uwm_conv2d_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int x_pitch, const void* d_wgt,
+                             const float* d_bias, int relu, void* d_y, int y_pitch, void* stream);
+
+/* The segmentation head on such a space-to-depth tensor: x[n,h,w,4*16] -> logits fp32 [n,2h,2w] / mask uint8
+ * [n,2h,2w] (either may be NULL).  wgt: UWM_PACK_S2D_CONV of the [1,16,3,3] head conv, [16][9*64]. */
+int uwm_head_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int x_pitch, const void* d_wgt,
+                           const float* d_bias, float* d_logits, int apply_sigmoid, uint8_t* d_mask,
+                           float thr_logit, void* stream);
 
 /* Segmentation head: conv3x3(cin -> 1, bias) + optional sigmoid + threshold + uint8 mask.
  * Replaces smp SegmentationHead and `(mask > thr)*255`

@@ -80,3 +80,12 @@ SPX_CASES = [
     ("spx_n256",               1, 16, 32, 128, 64, 64, True),      # N = 256 (one sub-tile, 2 x 256 TMEM columns)
     ("spx_persistent",         2, 128, 128, 64, 64, 32, True),     # several tiles per CTA
 ]
+
+# conv3x3 / head on a 16-channel tensor kept space-to-depth ([n,h,w,4x16] for [n,2h,2w,16]) -
+# uwm_conv2d_s2d_nhwc_bf16 / uwm_head_s2d_nhwc_bf16.   (name, n, h_blocks, w_blocks, relu)
+S2D_CASES = [
+    ("s2d_small",       1, 16, 16, True),
+    ("s2d_ragged",      2, 12, 20, False),      # 24x40 pixels: partial tiles on both axes
+    ("s2d_wide",        1, 16, 64, True),       # several sub-tiles per tile
+    ("s2d_persistent",  2, 128, 128, True),     # 256x256 pixels, several tiles per CTA
+]

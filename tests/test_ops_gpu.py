@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.op_cases import CONV_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES
+from tests.op_cases import CONV_CASES, S2D_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES
 from unet_watermark_b200 import _lib, ops, packing
 
 pytestmark = pytest.mark.gpu
@@ -123,6 +123,57 @@ def test_upcat_subpixel_conv_matches_fp32_reference(case, cuda_device):
     ref = ref.permute(0, 2, 3, 1)
     err = (out.float() - ref).abs()
     assert bool((err <= 1.5e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+
+
+def _s2d_nhwc(x):
+    """[N,2h,2w,C] -> [N,h,w,4C], channel (ph*2+pw)*C + c."""
+    n, hh, ww, c = x.shape
+    return x.reshape(n, hh // 2, 2, ww // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, hh // 2, ww // 2, 4 * c).contiguous()
+
+
+@pytest.mark.parametrize("case", S2D_CASES, ids=[c[0] for c in S2D_CASES])
+def test_s2d_conv_matches_fp32_reference(case, cuda_device):
+    """conv3x3 on a 16-channel tensor stored space-to-depth vs F.conv2d at full resolution on the same bf16 inputs and
+    weights (the packing copies weights, so only fp32 accumulation order and the bf16 output rounding differ:
+    |err| <= 1e-2 * max(1, |ref|), the per-op tolerance of the other conv tests)."""
+    name, n, h, w, relu = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(n, 2 * h, 2 * w, 16, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(16, 16, 3, 3, generator=g) / 12).to(dev)
+    bias = torch.randn(16, generator=g).to(dev)
+    before = _lib.load().uwm_kernel_launch_count()
+    out = ops.conv2d_s2d(_s2d_nhwc(x), packing.pack_s2d_conv3x3(wt), bias.repeat(4).contiguous(), relu=relu)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=1)
+    if relu:
+        ref = ref.relu()
+    ref = _s2d_nhwc(ref.permute(0, 2, 3, 1).contiguous())
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+
+
+@pytest.mark.parametrize("case", S2D_CASES, ids=[c[0] for c in S2D_CASES])
+def test_s2d_head_matches_fp32_reference(case, cuda_device):
+    """Head on the space-to-depth tensor: fp32 logits within 2e-3 of F.conv2d on the same bf16 inputs / weights, the
+    uint8 mask bit-exact wherever the reference logit is further than that from the threshold."""
+    name, n, h, w, _ = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000 + 1)
+    x = torch.randn(n, 2 * h, 2 * w, 16, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(1, 16, 3, 3, generator=g) / 12).to(dev)
+    bias = torch.randn(1, generator=g).to(dev)
+    logits, mask = ops.head_s2d(_s2d_nhwc(x), packing.pack_s2d_conv3x3(wt, 16), packing.pad_bias(bias, 16), threshold=0.5)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=1)[:, 0]
+    assert logits.shape == ref.shape and mask.shape == ref.shape
+    assert (logits - ref).abs().max().item() <= 2e-3
+    sure = ref.abs() > 2e-3
+    assert torch.equal(mask[sure], ((ref > 0).to(torch.uint8) * 255)[sure])
+    assert set(mask.unique().tolist()) <= {0, 255}
+    # mask-only call (what predict_mask uses) gives the same bytes
+    _, mask2 = ops.head_s2d(_s2d_nhwc(x), packing.pack_s2d_conv3x3(wt, 16), packing.pad_bias(bias, 16), threshold=0.5,
+                            want_logits=False)
+    assert torch.equal(mask, mask2)
 
 
 def test_conv_rejects_bad_arguments(cuda_device):

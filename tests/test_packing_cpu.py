@@ -121,3 +121,62 @@ def test_upcat_subpixel_packing_equals_conv_on_upsample_concat():
         x0 = torch.zeros_like(x)
         ref0 = F.conv2d(torch.cat([F.interpolate(x0, scale_factor=2, mode="nearest"), skip], 1), wt, padding=1)
         assert torch.allclose(_emulate_upcat_subpixel(x0, skip, wp.float(), c_x, cout), ref0, atol=1e-4, rtol=1e-4)
+
+
+def _s2d(x):
+    """[N,C,2h,2w] -> [N,4C,h,w], channel (ph*2+pw)*C + c (the layout the sub-pixel conv's GEMM writes)."""
+    n, c, hh, ww = x.shape
+    return x.reshape(n, c, hh // 2, 2, ww // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, hh // 2, ww // 2)
+
+
+def _d2s(y, c):
+    n, _, h, w = y.shape
+    return y.reshape(n, 2, 2, c, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, c, 2 * h, 2 * w)
+
+
+def test_s2d_packing_equals_conv_at_full_resolution():
+    """conv3x3(x) == depth_to_space(conv3x3_over_blocks(space_to_depth(x), pack_s2d_conv3x3(w))), and the kernel only
+    issues the (block tap, parity plane) pairs that can meet: every other K slice of the packed matrix must be zero."""
+    g = torch.Generator().manual_seed(4)
+    for cout, rows in ((16, 0), (1, 16)):
+        cin = 16
+        w = (torch.randn(cout, cin, 3, 3, generator=g) / 12).to(torch.bfloat16).float()
+        x = torch.randn(2, cin, 10, 12, generator=g)
+        ref = F.conv2d(x, w, padding=1)
+        wp = packing.pack_s2d_conv3x3(w, rows)
+        assert wp.shape == (max(rows, 4 * cout), 9 * 4 * cin) and wp.dtype == torch.bfloat16
+        wk = wp.float().reshape(-1, 3, 3, 4 * cin).permute(0, 3, 1, 2)              # [(q,co), (p,ci), r, c]
+        y = F.conv2d(_s2d(x), wk, padding=1)[:, :4 * cout]
+        assert torch.allclose(_d2s(y, cout), ref, atol=1e-5, rtol=1e-5)
+        # weights are copied, never summed: the set of non-zero values is exactly w's
+        assert set(wp.float().unique().tolist()) <= set(w.unique().tolist()) | {0.0}
+        wv = wp.float().reshape(-1, 3, 3, 2, 2, cin)                                  # [row, r, c, ph, pw, ci]
+        for r in range(3):
+            for c in range(3):
+                for ph in range(2):
+                    for pw in range(2):
+                        meets = r in (1 - ph, 2 - ph) and c in (1 - pw, 2 - pw)
+                        if not meets:
+                            assert not wv[:, r, c, ph, pw].any(), (r, c, ph, pw)
+
+
+def test_subpixel_then_s2d_chain_matches_reference_block():
+    """Decoder block 4 as the plan runs it: conv1 = sub-pixel conv WITHOUT the pixel shuffle (its GEMM output is the
+    space-to-depth layout), conv2 and the head consume that layout directly."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 32, 6, 8, generator=g)
+    w1 = torch.randn(16, 32, 3, 3, generator=g) / 17
+    w2 = torch.randn(16, 16, 3, 3, generator=g) / 12
+    wh = torch.randn(1, 16, 3, 3, generator=g) / 12
+    t = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w1, padding=1).relu()
+    t = F.conv2d(t, w2, padding=1).relu()
+    ref = F.conv2d(t, wh, padding=1)
+    k1 = packing.pack_up2x_shuffle_f32(w1).reshape(64, 3, 3, 32).permute(0, 3, 1, 2)
+    k2 = packing.pack_s2d_conv3x3(w2.to(torch.bfloat16).float()).float().reshape(64, 3, 3, 64).permute(0, 3, 1, 2)
+    kh = packing.pack_s2d_conv3x3(wh.to(torch.bfloat16).float(), 16).float().reshape(16, 3, 3, 64).permute(0, 3, 1, 2)
+    s = F.conv2d(x, k1, padding=1).relu()                      # [1, 4x16, 6, 8] == s2d of conv1's output
+    assert torch.allclose(_d2s(s, 16), F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w1, padding=1).relu(),
+                          atol=1e-4, rtol=1e-4)
+    s = F.conv2d(s, k2, padding=1).relu()
+    z = F.conv2d(s, kh, padding=1)[:, :4]
+    assert torch.allclose(_d2s(z, 1), ref, atol=2e-2, rtol=0)   # w2 / wh rounded to bf16 on this side only

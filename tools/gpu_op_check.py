@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.op_cases import CONV_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES  # noqa: E402
+from tests.op_cases import CONV_CASES, S2D_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES  # noqa: E402
 from unet_watermark_b200 import ops, packing  # noqa: E402
 
 
@@ -140,6 +140,45 @@ def main():
         except Exception as ex:  # noqa: BLE001
             nfail += 1
             print(f"EXC  subpx {case[0]}: {ex}", flush=True)
+            traceback.print_exc()
+            if "CUDA" in str(ex) or "fault" in str(ex):
+                print("aborting after CUDA error")
+                sys.exit(2)
+
+    def s2d_nhwc(x):
+        n, hh, ww, c = x.shape
+        return x.reshape(n, hh // 2, 2, ww // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, hh // 2, ww // 2, 4 * c).contiguous()
+
+    for case in S2D_CASES:
+        if args.filter not in case[0]:
+            continue
+        try:
+            name, n, h, w, relu = case
+            g = torch.Generator(device="cpu").manual_seed(0)
+            x = torch.randn(n, 2 * h, 2 * w, 16, generator=g).to(dev).to(torch.bfloat16)
+            wt = (torch.randn(16, 16, 3, 3, generator=g) / 12).to(dev)
+            bias = torch.randn(16, generator=g).to(dev)
+            out = ops.conv2d_s2d(s2d_nhwc(x), packing.pack_s2d_conv3x3(wt), bias.repeat(4).contiguous(), relu=relu)
+            torch.cuda.synchronize()
+            ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=1)
+            ref = s2d_nhwc((ref.relu() if relu else ref).permute(0, 2, 3, 1).contiguous())
+            err = (out.float() - ref).abs()
+            bad = (err > 1e-2 * ref.abs().clamp_min(1.0)).float().mean().item()
+            print(f"{'OK  ' if bad == 0 else 'FAIL'} s2d   {name:<24s} max_err={err.max().item():.4g} ref_max={ref.abs().max().item():.4g} bad_frac={bad:.4g}", flush=True)
+            nfail += (bad != 0)
+            wh = (torch.randn(1, 16, 3, 3, generator=g) / 12).to(dev)
+            bh = torch.randn(1, generator=g).to(dev)
+            logits, mask = ops.head_s2d(s2d_nhwc(x), packing.pack_s2d_conv3x3(wh, 16), packing.pad_bias(bh, 16), threshold=0.5)
+            torch.cuda.synchronize()
+            refh = F.conv2d(x.float().permute(0, 3, 1, 2), wh.to(torch.bfloat16).float(), bh, padding=1)[:, 0]
+            e = (logits - refh).abs().max().item()
+            sure = refh.abs() > 2e-3
+            okm = bool(torch.equal(mask[sure], ((refh > 0).to(torch.uint8) * 255)[sure]))
+            print(f"{'OK  ' if (e <= 2e-3 and okm) else 'FAIL'} s2dhd {name:<24s} max_err={e:.4g} mask_ok={okm}", flush=True)
+            nfail += (not (e <= 2e-3 and okm))
+        except Exception as ex:  # noqa: BLE001
+            nfail += 1
+            print(f"EXC  s2d {case[0]}: {ex}", flush=True)
             traceback.print_exc()
             if "CUDA" in str(ex) or "fault" in str(ex):
                 print("aborting after CUDA error")

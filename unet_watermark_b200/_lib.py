@@ -20,6 +20,7 @@ PACK_TAPS = 0
 PACK_STEM_S2D = 1
 PACK_UP2X_SHUFFLE = 2
 PACK_UPCAT_SUBPIXEL = 3
+PACK_S2D_CONV = 4
 
 
 class LayerDesc(C.Structure):
@@ -52,6 +53,8 @@ SIGNATURES = {
                                                     C.c_int, _P, C.c_int, _P]),
     "uwm_conv2d_upcat_subpixel_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int,
                                                       C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "uwm_conv2d_s2d_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
+    "uwm_head_s2d_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_float, _P]),
     "uwm_head_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,
                                      _P, C.c_float, _P]),
     "uwm_maxpool3x3s2_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),

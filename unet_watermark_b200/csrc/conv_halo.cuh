@@ -184,7 +184,14 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 // 3x3 block neighbourhood: 16 (plane, tap) pairs instead of the 36 a dense 3x3 conv over the space-to-depth input
 // would issue.  Weight slices stream in issue order (p.spx_slices per tile, one per stage); in SPX kernels tm_out and
 // tm_res are the weight maps with half- and quarter-height boxes (the epilogue stores without TMA).
-template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, bool SPX = false>
+//
+// S2D (conv3x3 on a tensor stored space-to-depth): a [n, 2h, 2w, 16] activation kept as [n, h, w, 4 x 16] (channel
+// group = pixel parity (ph,pw), the layout the sub-pixel conv's GEMM produces before any pixel shuffle) is one
+// 64-channel chunk whose K=16 slice k IS parity plane k.  A 3x3 conv at the full resolution is then a 3x3 conv over
+// blocks with 4x16 outputs in which plane (ph,pw) only meets taps {1-ph,2-ph} x {1-pw,2-pw}: the MMA loop issues those
+// 16 of the 36 (tap, k) pairs (N = 64 or 16 instead of 16 per MMA, 2.25x fewer MMAs per output pixel) and rows of
+// 128 bytes go in and out by TMA.  The head variant writes the 4 logits / mask bytes of a block to its 2x2 pixels.
+template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, bool SPX = false, bool S2D = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -383,7 +390,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               for (int g = 0; g < TG; ++g) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
-                  if (tap == 0 && k == 0)
+                  if (S2D) {       // parity plane k = (ph,pw) meets taps {1-ph,2-ph} x {1-pw,2-pw} only (folds at compile time)
+                    const int r = R0 + tap / NC, c = C0 + tap % NC, ph = k >> 1, pw = k & 1;
+                    if (!((r == 1 - ph || r == 2 - ph) && (c == 1 - pw || c == 2 - pw))) continue;
+                  }
+                  if (tap == 0 && k == (S2D ? 3 : 0))
                     umma_halo<false>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
                                      b_lo + 2u * k, b_hi, idesc, (uint32_t)ch);
                   else
@@ -514,7 +525,37 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       if (p.dbg & 4) {
         // bench-only: no epilogue work
       } else if (p.head) {
-        if (TG >= 2 || eset == 0) {
+        if (S2D) {
+          // 4 GEMM columns = the 2x2 output pixels of this block: logits / mask rows 2*oh + qh, columns 2*ow + qw
+          if (TG >= 2 || eset == 0) {
+            uint32_t z[GN][4];
+#pragma unroll
+            for (int gi = 0; gi < GN; ++gi) tmem_ld_x4(taddr0 + (uint32_t)(GSTEP * gi + g_first) * bn, z[gi]);
+            tmem_ld_wait();
+            const float b = __ldg(p.bias);
+            const bool pair_ok = ((reinterpret_cast<uintptr_t>(p.mask) & 1) == 0);
+#pragma unroll
+            for (int gi = 0; gi < GN; ++gi) {
+              const int g = GSTEP * gi + g_first;
+              if (row_ok && ow0 + g * kHaloTW < p.w) {
+#pragma unroll
+                for (int qh = 0; qh < 2; ++qh) {
+                  const long long o = ((long long)(t.img * 2 * p.h + 2 * oh + qh) * (2 * p.w)) + 2 * (ow0 + g * kHaloTW);
+                  const float z0 = __uint_as_float(z[gi][2 * qh]) + b, z1 = __uint_as_float(z[gi][2 * qh + 1]) + b;
+                  if (p.logits) {
+                    p.logits[o] = p.apply_sigmoid ? 1.f / (1.f + __expf(-z0)) : z0;
+                    p.logits[o + 1] = p.apply_sigmoid ? 1.f / (1.f + __expf(-z1)) : z1;
+                  }
+                  if (p.mask) {
+                    const uint8_t m0 = (z0 > p.thr_logit) ? 255 : 0, m1 = (z1 > p.thr_logit) ? 255 : 0;
+                    if (pair_ok) *reinterpret_cast<uchar2*>(p.mask + o) = make_uchar2(m0, m1);
+                    else { p.mask[o] = m0; p.mask[o + 1] = m1; }
+                  }
+                }
+              }
+            }
+          }
+        } else if (TG >= 2 || eset == 0) {
           uint32_t z[GN];
 #pragma unroll
           for (int gi = 0; gi < GN; ++gi) tmem_ld_x1(taddr0 + (uint32_t)(GSTEP * gi + g_first) * bn, z[gi]);

@@ -140,6 +140,7 @@ struct ConvSpec {
   void* out = nullptr;
   long long out_pitch = 0;
   int shuffle = 0;                // sub-pixel conv: real cout; `cout`/`cout_pad` are then 4x that (one group per output parity)
+  int s2d = 0;                    // x (and out, or the head's 4 logits per block) are space-to-depth: [n,h,w,4*16], see conv_halo.cuh S2D
   int head = 0, apply_sigmoid = 0;
   float* logits = nullptr;
   uint8_t* mask = nullptr;
@@ -148,7 +149,7 @@ struct ConvSpec {
 
 struct ConvLaunch {
   int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
-  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0, spx = 0;   // halo: template instantiation
+  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0, spx = 0, s2d = 0;   // halo: template instantiation
   CUtensorMap tm_act, tm_wgt, tm_out, tm_res, tm_a0, tm_a1;
   ConvKArgs args;
   HaloKArgs hargs;
@@ -327,7 +328,10 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   if (s.res && ((s.res_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.res) & 15)))
     return fail(UWM_EINVAL, "halo conv: residual base/pitch must be 16-byte aligned");
 
+  if (s.s2d && (s.cin != 64 || s.x2 || s.up1 || s.ntaps != 9 || s.res || s.shuffle || (s.head ? s.cout_pad != 16 : s.cout_pad != 64)))
+    return fail(UWM_EINVAL, "halo conv: space-to-depth form needs 4x16 input channels, one source, 3x3, 4x16 outputs (or the head)");
   L->halo = 1;
+  L->s2d = s.s2d ? 1 : 0;
   HaloKArgs& a = L->hargs;
   memset(&a, 0, sizeof(a));
   a.n_img = s.n; a.h = s.h; a.w = s.w;
@@ -400,11 +404,12 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const int n_tiles = s.cout_pad / bn;
       const bool resident = (n_tiles == 1) && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
       if (!resident && (tg > 2 || 2 * b_slice + 2 * a_stage > kBudget)) break;   // streamed kernels: TG 1, 2
+      if (s.s2d && (!resident || tg > 4 || !a_tma)) break;         // S2D: resident weights, TG 1, 2, 4, TMA-fed
       if (kh == 4 && !resident) break;
       if (kh == 1 && (tg > 4 || !a_tma)) break;                    // 1x1: TG 1, 2, 4, TMA-fed only
       const long long tiles = (long long)((s.w + kHaloTW * tg - 1) / (kHaloTW * tg)) * ((s.h + kHaloTH - 1) / kHaloTH) * s.n * n_tiles;
       const long long waves = (tiles + sms - 1) / sms;
-      const double mmas = (double)tg * nk * (kc / 16);
+      const double mmas = (double)tg * nk * (kc / 16) * (s.s2d ? 16.0 / 36.0 : 1.0);   // S2D skips the (tap, plane) pairs that cannot meet
       const double tensor = mmas * (bn >= 256 ? 128.0 : 32.0 + bn / 4.0);   // measured: operand fetch (128+N)x32 B at 128 B/clk
       const double issue = 6.0 * (60.0 * a.chunks + 12.0 * nk + 3.0 * mmas);
       const double a_bytes = (double)halo_npix(tg, kh, kw) * cin_total * 2;
@@ -681,7 +686,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   if (!L) {                                                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES, AT>,                                    \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                    \
-  } else if (!L->spx && L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES && \
+  } else if (!L->spx && !L->s2d && L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES && \
              (L->a_tma != 0) == AT) {                                                                           \
     launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
                L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                                                   \
@@ -700,6 +705,19 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   UWM_HALO_CASE1(64, 1, 1, 1, false, true) UWM_HALO_CASE1(64, 1, 1, 2, false, true)
 #undef UWM_HALO_CASE
 #undef UWM_HALO_CASE1
+  // space-to-depth 3x3 convs (S2D): one 64-channel chunk = 4 parity planes x 16, resident weights, TMA-fed
+#define UWM_HALO_S2D(TG)                                                                                          \
+  if (!L) {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, true, true, false, true>,                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
+  } else if (L->s2d && L->tg == TG && L->kc == 64 && L->resident && L->a_tma) {                                   \
+    launch_pdl(conv_halo_kernel<64, 3, 3, TG, true, true, false, true>, L->grid, kHaloThreads, L->smem, st,       \
+               L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                    \
+    return UWM_OK;                                                                                                \
+  }
+  UWM_HALO_S2D(1) UWM_HALO_S2D(2) UWM_HALO_S2D(4)
+#undef UWM_HALO_S2D
+  if (L && L->s2d) return fail(UWM_ESTATE, "halo conv: no space-to-depth kernel for tg=%d resident=%d", L->tg, L->resident);
   // sub-pixel upcat conv (SPX): 64-channel chunks, streamed weights, TMA-fed
 #define UWM_HALO_SPX(TG)                                                                                          \
   if (!L) {                                                                                                       \
@@ -855,6 +873,37 @@ extern "C" int uwm_head_nhwc_bf16(const void* d_x, int n, int h, int w, int cin,
   return launch_conv(L, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int uwm_conv2d_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int x_pitch, const void* d_wgt,
+                                        const float* d_bias, int relu, void* d_y, int y_pitch, void* stream) {
+  if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_s2d: null pointer");
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = 64; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = 64; s.cout_pad = 64; s.s2d = 1;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 1; s.h_out = h; s.w_out = w;
+  s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_halo(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uwm_head_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int x_pitch, const void* d_wgt,
+                                      const float* d_bias, float* d_logits, int apply_sigmoid, uint8_t* d_mask,
+                                      float thr_logit, void* stream) {
+  if (!d_x || !d_wgt || !d_bias) return fail(UWM_EINVAL, "head_s2d: null pointer");
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = 64; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = 1; s.cout_pad = 16; s.s2d = 1;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 1; s.h_out = h; s.w_out = w;
+  s.head = 1; s.apply_sigmoid = apply_sigmoid; s.logits = d_logits; s.mask = d_mask; s.thr_logit = thr_logit;
+  ConvLaunch L;
+  int rc = build_halo(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
 static int launch_maxpool(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
                           cudaStream_t st) {
   if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
@@ -911,6 +960,7 @@ struct Buf {
 };
 struct TRef {            // a [B,h,w,c] bf16 view: channels [c_off, c_off+c) of a pitch-wide buffer
   int buf = -1, c_off = 0, c = 0, pitch = 0, h = 0, w = 0;
+  bool s2d = false;      // stores a [B,2h,2w,c/4] tensor space-to-depth: channel = (ph*2+pw)*(c/4) + ch
 };
 enum OpType { OP_PREP, OP_CONV, OP_HEAD, OP_POOL };
 struct Op {
@@ -928,6 +978,7 @@ struct Layer {
   uwm_layer_desc d;
   bool stem = false;
   bool shuffle = false;    // decoder conv1 without a skip: 3x3 conv on the upsampled input as a sub-pixel conv
+  bool s2d = false;        // 3x3 conv over a space-to-depth tensor (conv_halo.cuh S2D); d.cin/d.cout stay the reference's
   void* d_w = nullptr;
   float* d_b = nullptr;
   bool set = false;
@@ -990,7 +1041,7 @@ struct uwm_model {
 
 static int add_layer(uwm_model* m, const std::string& conv_key, const std::string& bn_key, int cin,
                      int cout, int k, int stride, int pad, int relu, int has_res, bool stem = false,
-                     bool shuffle = false, int spx_cskip = 0) {
+                     bool shuffle = false, int spx_cskip = 0, bool s2d = false) {
   Layer L;
   memset(&L.d, 0, sizeof(L.d));
   snprintf(L.d.conv_key, sizeof(L.d.conv_key), "%s", conv_key.c_str());
@@ -1002,6 +1053,12 @@ static int add_layer(uwm_model* m, const std::string& conv_key, const std::strin
   if (stem) {
     L.d.pack = UWM_PACK_STEM_S2D;
     L.d.w_elems = (int64_t)L.d.cout_pad * 16 * 16;
+  } else if (s2d) {
+    // 3x3 conv on a [.,2h,2w,16] tensor kept as [.,h,w,4x16]: 4*cout GEMM columns (16 for the 1-channel head), K = 9 x 64
+    L.s2d = true;
+    L.d.pack = UWM_PACK_S2D_CONV;
+    L.d.cout_pad = (cout == 1) ? 16 : 4 * cout;
+    L.d.w_elems = (int64_t)L.d.cout_pad * 9 * 4 * cin;
   } else if (shuffle && spx_cskip > 0) {
     // decoder conv1 WITH a skip, sub-pixel form: see build_halo_spx
     L.shuffle = true;
@@ -1036,7 +1093,7 @@ static void add_conv(uwm_model* m, int layer, const TRef& in, const TRef& out, c
   if (res) { op.res = *res; op.has_res = true; }
   if (in2) { op.in2 = *in2; op.has_in2 = true; }
   if (head) { op.out.h = out_h; op.out.w = out_w; }
-  const double px = (double)op.out.h * op.out.w;
+  const double px = (double)op.out.h * op.out.w * (op.out.s2d ? 4.0 : 1.0);   // pixels of the reference's output
   op.flops_per_img = 2.0 * d.cin * d.cout * d.kh * d.kw * px;
   // algorithmic bytes: every source read once at its stored resolution, output written once
   double in_bytes = m->layers[layer].stem ? 2.0 * in.h * in.w * 16 : 2.0 * (double)in.h * in.w * in.c;
@@ -1134,10 +1191,18 @@ static int build_plan(uwm_model* m) {
   }
 
   // ---- decoder ----
+  bool s2d_tail = false;
   for (int i = 0; i < 5; ++i) {
     const int bh = H >> (4 - i), bw = W >> (4 - i);
     const std::string pre = fmt("decoder.blocks.%d", i);
-    TRef t1 = m->dense(bh, bw, dec[i]);
+    // Block 4 of the default decoder (16 channels at the input resolution, no skip): both tensors of the block stay
+    // space-to-depth [bh/2, bw/2, 4x16] - conv1's sub-pixel GEMM output as it is (no pixel shuffle), conv2 and the
+    // head as S2D convs - so every row is 128 bytes (TMA in and out) and the MMAs have N = 64 instead of 16.
+    static const bool s2d_on = []{ const char* e = getenv("UWM_S2D"); return !(e && e[0] == '0'); }();
+    const bool s2d = (i == 4) && s2d_on && subpixel_enabled() && cs[i] == 0 && dec[i] == 16;
+    s2d_tail = s2d;
+    TRef t1 = s2d ? m->dense(bh / 2, bw / 2, 4 * dec[i]) : m->dense(bh, bw, dec[i]);
+    t1.s2d = s2d;
     // sub-pixel forms (N = 4*cout <= 256 on the source grid): without a skip, and with a skip when both sources
     // split into 64-channel chunks (build_halo_spx)
     static const bool spx_on = []{ const char* e = getenv("UWM_SPX"); return !(e && e[0] == '0'); }();
@@ -1147,14 +1212,15 @@ static int build_plan(uwm_model* m) {
     int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0, false, subpixel,
                        spx ? cs[i] : 0);
     add_conv(m, l1, x, t1, nullptr, false, /*up=*/true, cs[i] ? &skip[i] : nullptr);
-    TRef t2 = m->dense(bh, bw, dec[i]);
-    int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0);
+    TRef t2 = s2d ? m->dense(bh / 2, bw / 2, 4 * dec[i]) : m->dense(bh, bw, dec[i]);
+    t2.s2d = s2d;
+    int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0, false, false, 0, s2d);
     add_conv(m, l2, t1, t2, nullptr);
     x = t2;
     m->named[pre] = x;
   }
   // ---- head ----
-  int lh = add_layer(m, "segmentation_head.0", "", dec[4], 1, 3, 1, 1, 0, 0);
+  int lh = add_layer(m, "segmentation_head.0", "", dec[4], 1, 3, 1, 1, 0, 0, false, false, 0, s2d_tail);
   TRef none;
   add_conv(m, lh, x, none, nullptr, /*head=*/true, false, nullptr, H, W);
 
@@ -1291,10 +1357,14 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
           s.h_out = op.in.h; s.w_out = op.in.w;
         } else {
           s.cin = op.in.c; s.stride = ly.d.stride;
-          if (ly.shuffle) { s.shuffle = ly.d.cout; s.cout = ly.d.cout_pad; }   // runs on the source grid, N = 4*cout
+          if (ly.s2d) { s.s2d = 1; if (op.type != OP_HEAD) s.cout = ly.d.cout_pad; }
+          if (ly.shuffle) {   // runs on the source grid, N = 4*cout; a space-to-depth output keeps the GEMM layout
+            s.cout = ly.d.cout_pad;
+            if (!op.out.s2d) s.shuffle = ly.d.cout;
+          }
           else if (op.up) { s.up1 = 1; s.h = op.in.h * 2; s.w = op.in.w * 2; }
           if (op.has_in2) { s.x2 = m->ptr(op.in2); s.cin2 = op.in2.c; s.x2_pitch = op.in2.pitch; }
-          if (s.cin + s.cin2 != ly.d.cin)
+          if (s.cin + s.cin2 != (ly.s2d ? 4 : 1) * ly.d.cin)
             return fail(UWM_ESTATE, "plan bug: %s reads %d+%d channels, layer has %d", ly.d.conv_key, s.cin, s.cin2, ly.d.cin);
           taps_rect(&s, ly.d.kh, ly.d.kw, ly.d.pad);
           s.h_out = (s.h + 2 * ly.d.pad - ly.d.kh) / ly.d.stride + 1;
@@ -1304,7 +1374,7 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
         if (op.type == OP_HEAD) {
           s.head = 1; s.apply_sigmoid = apply_sigmoid; s.logits = d_logits; s.mask = d_mask; s.thr_logit = thr_logit;
         } else {
-          const int up_out = ly.shuffle ? 2 : 1;       // the sub-pixel conv writes a 2x larger tensor
+          const int up_out = (ly.shuffle && !op.out.s2d) ? 2 : 1;   // the pixel-shuffling sub-pixel conv writes a 2x larger tensor
           if (s.h_out * up_out != op.out.h || s.w_out * up_out != op.out.w)
             return fail(UWM_ESTATE, "plan bug: %s output %dx%d != planned %dx%d", ly.d.conv_key, s.h_out * up_out,
                         s.w_out * up_out, op.out.h, op.out.w);
@@ -1423,17 +1493,40 @@ __global__ void gather_pitched_kernel(const __nv_bfloat16* __restrict__ src, __n
   }
 }
 
+// a space-to-depth plan tensor [px(h,w)][4 x c4] read back as dense [2h][2w][c4]
+__global__ void gather_d2s_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n, int h,
+                                  int w, int c4, long long pitch) {
+  const int cg = c4 / 8;
+  const long long total = (long long)n * 2 * h * 2 * w * cg;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long px = idx / cg;
+    const int x = (int)(px % (2 * w)); px /= 2 * w;
+    const int y = (int)(px % (2 * h)); const int img = (int)(px / (2 * h));
+    const long long sp = ((long long)img * h + (y >> 1)) * w + (x >> 1);
+    *reinterpret_cast<uint4*>(dst + (idx / cg) * c4 + g * 8) =
+        *reinterpret_cast<const uint4*>(src + sp * pitch + ((y & 1) * 2 + (x & 1)) * c4 + g * 8);
+  }
+}
+
 extern "C" int uwm_model_read_tensor(uwm_model* m, const char* name, int batch, void* d_dst, int64_t dst_bytes,
                                      int* h, int* w, int* c, void* stream) {
   if (!m || !name) return fail(UWM_EINVAL, "read_tensor: null argument");
   auto it = m->named.find(name);
   if (it == m->named.end()) return fail(UWM_EINVAL, "read_tensor: unknown tensor '%s'", name);
   const TRef& t = it->second;
-  if (h) *h = t.h; if (w) *w = t.w; if (c) *c = t.c;
+  const int up = t.s2d ? 2 : 1;
+  if (h) *h = t.h * up; if (w) *w = t.w * up; if (c) *c = t.c / (up * up);
   if (!d_dst) return UWM_OK;
   const long long px = (long long)batch * t.h * t.w;
   if (dst_bytes < px * t.c * 2) return fail(UWM_EINVAL, "read_tensor: destination too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (t.s2d) {
+    gather_d2s_kernel<<<stream_grid(px * (t.c / 8), 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(m->ptr(t)), static_cast<__nv_bfloat16*>(d_dst), batch, t.h, t.w, t.c / 4, t.pitch);
+    return post_launch("gather_d2s_kernel", st);
+  }
   gather_pitched_kernel<<<stream_grid(px * (t.c / 8), 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(m->ptr(t)), static_cast<__nv_bfloat16*>(d_dst), px, t.c, t.pitch);
   return post_launch("gather_pitched_kernel", st);

@@ -128,6 +128,44 @@ def head(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, threshold:
     return logits, mask
 
 
+def conv2d_s2d(x: torch.Tensor, w_s2d: torch.Tensor, bias4: torch.Tensor, relu: bool = True,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv3x3 'same' on a 16-channel tensor kept space-to-depth: x, out = [N,h,w,64] standing for [N,2h,2w,16].
+    w_s2d: packing.pack_s2d_conv3x3(w) = [64, 9*64] bf16; bias4: bias repeated 4x (fp32)."""
+    _require_cuda(x, w_s2d, bias4, out)
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    if c != 64 or tuple(w_s2d.shape) != (64, 9 * 64):
+        raise ValueError(f"conv2d_s2d needs x [N,h,w,64] and weights [64, 576], got {tuple(x.shape)}, {tuple(w_s2d.shape)}")
+    if out is None:
+        out = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_s2d_nhwc_bf16(x.data_ptr(), n, h, w, _pitch(x), w_s2d.data_ptr(), bias4.data_ptr(), int(relu),
+                                      out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_s2d_nhwc_bf16")
+    return out
+
+
+def head_s2d(x: torch.Tensor, w_s2d: torch.Tensor, bias: torch.Tensor, threshold: Optional[float] = 0.5,
+             thr_on_logits: bool = False, want_logits: bool = True, apply_sigmoid: bool = False):
+    """The head on a space-to-depth tensor x [N,h,w,64] -> (fp32 logits [N,2h,2w] or None, uint8 mask or None).
+    w_s2d: packing.pack_s2d_conv3x3(w_head, 16) = [16, 9*64] bf16."""
+    _require_cuda(x, w_s2d, bias)
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    if c != 64 or tuple(w_s2d.shape) != (16, 9 * 64):
+        raise ValueError(f"head_s2d needs x [N,h,w,64] and weights [16, 576], got {tuple(x.shape)}, {tuple(w_s2d.shape)}")
+    logits = torch.empty(n, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if want_logits else None
+    mask = torch.empty(n, 2 * h, 2 * w, dtype=torch.uint8, device=x.device) if threshold is not None else None
+    thr_logit = 0.0
+    if threshold is not None:
+        thr_logit = float(threshold) if thr_on_logits else logit(threshold)
+    rc = lib.uwm_head_s2d_nhwc_bf16(x.data_ptr(), n, h, w, _pitch(x), w_s2d.data_ptr(), bias.data_ptr(),
+                                    logits.data_ptr() if logits is not None else None, int(apply_sigmoid),
+                                    mask.data_ptr() if mask is not None else None, thr_logit, _stream())
+    _lib.check(rc, "uwm_head_s2d_nhwc_bf16")
+    return logits, mask
+
+
 def logit(p: float) -> float:
     """threshold on sigmoid(z) > p  <=>  z > log(p/(1-p))"""
     if p <= 0.0:

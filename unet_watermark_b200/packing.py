@@ -116,6 +116,36 @@ def pack_upcat_subpixel(w: torch.Tensor, c_x: int) -> torch.Tensor:
     return torch.cat(slices, dim=1).to(torch.bfloat16).contiguous()
 
 
+def pack_s2d_conv3x3(w: torch.Tensor, rows: int = 0) -> torch.Tensor:
+    """conv3x3 on a tensor stored space-to-depth (UWM_PACK_S2D_CONV).
+
+    The [.,2h,2w,Cin] input is kept as [.,h,w,4*Cin] with channel (ph*2+pw)*Cin + ci, the output likewise with row
+    (qh*2+qw)*Cout + co.  Output row 2i+qh reads input row 2i+qh+kr-1 = 2(i+r-1)+ph for block tap r, i.e. kernel row
+    kr = 2(r-1)+ph-qh+1 (zero when outside 0..2; same for columns).  Returns bf16 [max(rows, 4*Cout), 9*4*Cin] in
+    pack_taps order over blocks: K index (r*3+c)*4*Cin + (ph*2+pw)*Cin + ci.  Every weight of w appears in exactly
+    the slots whose (block tap, plane) pair meets - nothing is summed, so the values are bit-identical to pack_taps."""
+    cout, cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3)
+    wf = w.detach().float()
+    out = torch.zeros(2, 2, cout, 3, 3, 2, 2, cin, dtype=torch.float32, device=w.device)
+    for qh in range(2):
+        for qw in range(2):
+            for r in range(3):
+                for c in range(3):
+                    for ph in range(2):
+                        kr = 2 * (r - 1) + ph - qh + 1
+                        if not 0 <= kr <= 2:
+                            continue
+                        for pw in range(2):
+                            kc = 2 * (c - 1) + pw - qw + 1
+                            if 0 <= kc <= 2:
+                                out[qh, qw, :, r, c, ph, pw, :] = wf[:, :, kr, kc]
+    out = out.reshape(4 * cout, 9 * 4 * cin)
+    if rows > out.shape[0]:
+        out = torch.cat([out, torch.zeros(rows - out.shape[0], out.shape[1], device=w.device)], 0)
+    return out.to(torch.bfloat16).contiguous()
+
+
 def pad_bias(b: torch.Tensor, cout_pad: int) -> torch.Tensor:
     out = torch.zeros(cout_pad, dtype=torch.float32, device=b.device)
     out[: b.numel()] = b.detach().float()
