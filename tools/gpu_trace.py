@@ -52,7 +52,7 @@ def main():
         t0 = t[0]
         rel = lambda v: (v - t0) if v else None  # noqa: E731
         print(f"== {name}  (cycles since kernel start of CTA 0)")
-        print(f"prologue done {rel(t[1])}")
+        print(f"prologue done {rel(t[1])}   loader: reached griddepcontrol.wait {rel(t[2])}, passed it {rel(t[3])}")
         print("loader  stage: slot-free / copies-issued")
         for i in range(72):
             if t[16 + 2 * i]:

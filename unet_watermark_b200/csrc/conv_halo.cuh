@@ -244,16 +244,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) { halo_trace(p, 0); halo_trace_cta(p, 0); }
-  for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += kHaloThreads) s_bias[i] = __ldg(p.bias + i);
+  // The prologue is on every launch's critical path (the CTA cannot start before the previous kernel's CTA has left
+  // the SM): the ~45 barrier inits are spread over four threads of different warps, and the bias is staged by the
+  // epilogue warps after the block-wide sync (they have thousands of cycles before the first accumulator).
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), A_TMA ? 1 : kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
     mbar_init(bres_bar, 1);
-    for (int w = 0; w < 8; ++w) mbar_init(resbar(w), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
-    if (p.ep_tma || SPX) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
+    if (SPX) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
+  } else if (threadIdx.x == 64) {
+    for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
+    for (int w = 0; w < 8; ++w) mbar_init(resbar(w), 1);
+    fence_mbar_init();
+    if (p.ep_tma) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
+  } else if (threadIdx.x == kHaloLoaderWarp0 * 32) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), A_TMA ? 1 : kHaloLoaderThreads); mbar_init(aempty_bar(s), 1); }
+    fence_mbar_init();
     if (A_TMA) { tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); }
     else if (p.mix) tma_prefetch_desc(&tm_a1);
   }
@@ -490,6 +497,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const int c_first = (TG >= 2) ? 0 : 16 * eset, c_step = (TG >= 2) ? 16 : 32;
     const bool tma_out = p.ep_tma != 0;
     const int ewarp = (warp & 3) + 4 * eset;                                  // 0..7
+    // stage the bias (all 8 epilogue warps, then a named barrier among them)
+    for (int i = ewarp * 32 + lane; i < p.n_tiles * p.block_n; i += 256) s_bias[i] = __ldg(p.bias + i);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const uint32_t stg = stg_base + (uint32_t)ewarp * (32u * 128u);           // one 32-row x 128-byte buffer per warp
     // 128B swizzle of the 16-byte chunks of this lane's row: chunk index ^ (row & 7)
     const uint32_t my_row_off = (uint32_t)lane * 128u;
@@ -700,7 +710,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   } else {
     // ------------------------------------------------------------ activation loaders (4 warps)
     const int lt = threadIdx.x - kHaloLoaderWarp0 * 32;
+    if (lt == 0) halo_trace(p, 2);
     pdl_wait();                              // activations are written by the previous kernel
+    if (lt == 0) halo_trace(p, 3);
     int s = 0; uint32_t ph = 0;
     int nstage = 0;
     if (A_TMA) {
