@@ -61,6 +61,11 @@ extern "C" {
                                  2(r-1)+ph-qh+1, 2(c-1)+pw-qw+1] for block tap (r,c), zero outside the 3x3 kernel;
                                  bias = 4 copies.  The 1-channel head: rows 0..3 = the 4 output parities, padded
                                  to 16 rows (packing.pack_s2d_conv3x3)                                           */
+#define UWM_PACK_S2_PLANES 5   /* stride-2 3x3 conv (pad 1) over the input's four parity planes: [cout][9*cin] bf16 as
+                                 64-channel slices in the kernel's issue order - per plane (ph,pw), per 64-channel
+                                 chunk, per halo tap (r,c) with r in {1} (ph = 0) or {0,1} (ph = 1), c likewise:
+                                 w[co, ci, kr, kc], kr = 1 if ph == 0 else (0 if r == 0 else 2), kc likewise
+                                 (packing.pack_s2_planes); the same 9*cin values as UWM_PACK_TAPS, reordered      */
 #define UWM_PACK_STEM_S2D 1   /* 7x7/s2 stem as 4x4/s1 over the 2x2 space-to-depth input:
                                  [64][4*4][16] bf16, channel = (ph*2+pw)*3 + c, 12..15 zero      */
 
@@ -122,6 +127,15 @@ int uwm_conv2d_upcat_subpixel_nhwc_bf16(const void* d_x, int n, int h, int w, in
                                         const void* d_skip, int c_skip, int skip_pitch, const void* d_wgt,
                                         const float* d_bias, int cout, int relu, void* d_y, int y_pitch,
                                         void* stream);
+
+/* Stride-2 conv3x3 (pad 1) (+bias)(+ReLU): x[n,h,w,cin] (h, w even; cin, cout multiples of 64) -> y[n,h/2,w/2,cout].
+ * wgt: UWM_PACK_S2_PLANES.  The four parity planes of x arrive as dense TMA boxes (element stride 2); each kernel tap
+ * is a stride-1 tap on one plane, so the halo kernel's MMA loop runs unchanged.  Same products and K as
+ * uwm_conv2d_nhwc_bf16(stride 2), different fp32 summation order.  Replaces torchvision resnet.py BasicBlock.conv1 /
+ * Bottleneck.conv2 of the first block of layer2-4. */
+int uwm_conv2d_s2_planes_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                   const void* d_wgt, const float* d_bias, int cout, int relu, void* d_y,
+                                   int y_pitch, void* stream);
 
 /* conv3x3 'same' (+bias)(+ReLU) on a 16-channel tensor kept space-to-depth: x, y = [n,h,w,4*16] standing for
  * [n,2h,2w,16] (channel = (ph*2+pw)*16 + c, what uwm_conv2d_nhwc_bf16 with UWM_PACK_UP2X_SHUFFLE weights writes).

@@ -89,3 +89,13 @@ S2D_CASES = [
     ("s2d_wide",        1, 16, 64, True),       # several sub-tiles per tile
     ("s2d_persistent",  2, 128, 128, True),     # 256x256 pixels, several tiles per CTA
 ]
+
+# Stride-2 conv3x3 (pad 1) on the parity-plane halo kernel - uwm_conv2d_s2_planes_nhwc_bf16.
+# (name, n, h_in, w_in, cin, cout, relu)
+S2P_CASES = [
+    ("l2_0_conv1_s2planes",  1, 32, 32, 64, 128, True),       # r34 layer2.0.conv1 shape
+    ("l3_0_conv1_s2planes",  1, 16, 16, 128, 256, True),      # two N tiles
+    ("s2planes_ragged",      2, 24, 40, 64, 64, False),       # 12x20 output: partial tiles, bn = 64
+    ("s2planes_persistent",  2, 256, 256, 64, 128, True),     # several tiles per CTA
+    ("r50_l4_conv2_s2planes", 1, 16, 16, 512, 512, True),     # long K (72 slices), four N tiles
+]

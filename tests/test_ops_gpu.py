@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.op_cases import CONV_CASES, S2D_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES
+from tests.op_cases import CONV_CASES, S2D_CASES, S2P_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES
 from unet_watermark_b200 import _lib, ops, packing
 
 pytestmark = pytest.mark.gpu
@@ -123,6 +123,30 @@ def test_upcat_subpixel_conv_matches_fp32_reference(case, cuda_device):
     ref = ref.permute(0, 2, 3, 1)
     err = (out.float() - ref).abs()
     assert bool((err <= 1.5e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+
+
+@pytest.mark.parametrize("case", S2P_CASES, ids=[c[0] for c in S2P_CASES])
+def test_stride2_plane_conv_matches_fp32_reference(case, cuda_device):
+    """Stride-2 conv3x3 over the input's parity planes vs F.conv2d(stride=2) on the same bf16 inputs / weights, and
+    against the library's other stride-2 kernel (conv_tc) on the same data: |err| <= 1e-2 * max(1, |ref|)."""
+    name, n, h, w, cin, cout, relu = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    before = _lib.load().uwm_kernel_launch_count()
+    out = ops.conv2d_s2_planes(x, packing.pack_s2_planes(wt), bias, relu=relu)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    assert out.shape == (n, h // 2, w // 2, cout)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, stride=2, padding=1)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 * ref.abs().clamp_min(1.0)).all()), f"max err {err.max().item()}"
+    other = ops.conv2d(x, packing.pack_taps(wt), bias, 3, 3, 2, 1, relu=relu)
+    assert bool(((out.float() - other.float()).abs() <= 2e-2 * ref.abs().clamp_min(1.0)).all())
 
 
 def _s2d_nhwc(x):

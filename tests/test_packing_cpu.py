@@ -180,3 +180,31 @@ def test_subpixel_then_s2d_chain_matches_reference_block():
     s = F.conv2d(s, k2, padding=1).relu()
     z = F.conv2d(s, kh, padding=1)[:, :4]
     assert torch.allclose(_d2s(z, 1), ref, atol=2e-2, rtol=0)   # w2 / wh rounded to bf16 on this side only
+
+
+def test_s2_planes_packing_equals_stride2_conv():
+    """conv3x3(stride 2, pad 1) == sum over parity planes of stride-1 taps on a 2x2 block halo at origin -1, with the
+    slices in the order pack_s2_planes emits them (what the SPX==2 kernel issues)."""
+    g = torch.Generator().manual_seed(6)
+    cout, cin, h, w = 64, 128, 10, 12
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / 30).to(torch.bfloat16).float()
+    x = torch.randn(2, cin, h, w, generator=g)
+    ref = F.conv2d(x, wt, stride=2, padding=1)
+    wp = packing.pack_s2_planes(wt).float()
+    assert wp.shape == (cout, 9 * cin)
+    ho, wo = h // 2, w // 2
+    acc = torch.zeros(2, cout, ho, wo)
+    k = 0
+    for ph in range(2):
+        for pw in range(2):
+            for cc in range(cin // 64):
+                halo = F.pad(x[:, cc * 64:(cc + 1) * 64, ph::2, pw::2], (1, 0, 1, 0))    # block -1 in front
+                for r in ((1,) if ph == 0 else (0, 1)):
+                    for c in ((1,) if pw == 0 else (0, 1)):
+                        sl = wp[:, k * 64:(k + 1) * 64]
+                        k += 1
+                        acc += torch.einsum("ok,nkhw->nohw", sl, halo[:, :, r:r + ho, c:c + wo])
+    assert k * 64 == wp.shape[1]
+    assert torch.allclose(acc, ref, atol=1e-4, rtol=1e-4)
+    # a permutation of pack_taps' columns: same multiset of values per output channel
+    assert torch.equal(wp.sort(dim=1).values, packing.pack_taps(wt).float().sort(dim=1).values)

@@ -21,6 +21,7 @@ PACK_STEM_S2D = 1
 PACK_UP2X_SHUFFLE = 2
 PACK_UPCAT_SUBPIXEL = 3
 PACK_S2D_CONV = 4
+PACK_S2_PLANES = 5
 
 
 class LayerDesc(C.Structure):
@@ -53,6 +54,8 @@ SIGNATURES = {
                                                     C.c_int, _P, C.c_int, _P]),
     "uwm_conv2d_upcat_subpixel_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int,
                                                       C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "uwm_conv2d_s2_planes_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
+                                                 C.c_int, _P, C.c_int, _P]),
     "uwm_conv2d_s2d_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
     "uwm_head_s2d_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_float, _P]),
     "uwm_head_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,

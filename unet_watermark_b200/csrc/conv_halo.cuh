@@ -185,13 +185,18 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 // would issue.  Weight slices stream in issue order (p.spx_slices per tile, one per stage); in SPX kernels tm_out and
 // tm_res are the weight maps with half- and quarter-height boxes (the epilogue stores without TMA).
 //
+// SPX == 2 (stride-2 3x3 conv, pad 1) uses the same machinery with every chunk a parity plane of the one source:
+// output pixel (i,j) reads input rows 2i-1, 2i, 2i+1 = (block i-1, plane 1), (block i, plane 0), (block i, plane 1), so
+// with a 2x2 block halo at origin -1 plane ph meets halo rows {1} (ph = 0) or {0,1} (ph = 1): 9 (plane, tap) pairs,
+// one per kernel tap, each a full-N MMA group over a dense TMA-written stage - the stride never reaches the MMA.
+//
 // S2D (conv3x3 on a tensor stored space-to-depth): a [n, 2h, 2w, 16] activation kept as [n, h, w, 4 x 16] (channel
 // group = pixel parity (ph,pw), the layout the sub-pixel conv's GEMM produces before any pixel shuffle) is one
 // 64-channel chunk whose K=16 slice k IS parity plane k.  A 3x3 conv at the full resolution is then a 3x3 conv over
 // blocks with 4x16 outputs in which plane (ph,pw) only meets taps {1-ph,2-ph} x {1-pw,2-pw}: the MMA loop issues those
 // 16 of the 36 (tap, k) pairs (N = 64 or 16 instead of 16 per MMA, 2.25x fewer MMAs per output pixel) and rows of
 // 128 bytes go in and out by TMA.  The head variant writes the 4 logits / mask bytes of a block to its 2x2 pixels.
-template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, bool SPX = false, bool S2D = false>
+template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, int SPX = 0, bool S2D = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -252,7 +257,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     mbar_init(bres_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
-    if (SPX) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
+    if (SPX == 1) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
   } else if (threadIdx.x == 64) {
     for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
     for (int w = 0; w < 8; ++w) mbar_init(resbar(w), 1);
@@ -301,7 +306,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           int sl = 0, par = 0, cc = 0;       // no divisions here: this one thread feeds ~25 slices per tile
           for (int ch = 0; ch < p.chunks; ++ch) {
             const bool is_x = ch < p.split_chunk;
-            const int nt = is_x ? 9 : 4;
+            const int nt = (SPX == 2) ? ((par >> 1) + 1) * ((par & 1) + 1) : (is_x ? 9 : 4);
             for (int t = 0; t < nt; ++t, ++sl) {
               if (leader) {
                 int R, C;
@@ -311,12 +316,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                 } else {
                   R = 1 - (par >> 1) + (t >> 1); C = 1 - (par & 1) + (t & 1);
                 }
-                const int qn = (R == 1) ? 4 : (C == 1 ? 2 : 1);
-                const int qoff = (R == 1) ? 0 : 2 * (R == 2) + (C == 1 ? 0 : (C == 2));
+                const int qn = (SPX == 2 || R == 1) ? 4 : (C == 1 ? 2 : 1);
+                const int qoff = (SPX == 2 || R == 1) ? 0 : 2 * (R == 2) + (C == 1 ? 0 : (C == 2));
                 const CUtensorMap* tm = (qn == 4) ? &tm_wgt : (qn == 2 ? &tm_out : &tm_res);
                 mbar_wait(bempty_bar(s), ph ^ 1u);
                 mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)(qn * (p.block_n >> 2)) * KC * 2u);
-                tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, tm, bfull_bar(s), sl * KC, qoff * (p.block_n >> 2));
+                tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, tm, bfull_bar(s), sl * KC,
+                            (SPX == 2 ? ncol : 0) + qoff * (p.block_n >> 2));
               }
               if (++s == p.b_stages) { s = 0; ph ^= 1u; }
             }
@@ -356,8 +362,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const uint32_t b_stage_units = b_stage_bytes >> 4;
     const uint32_t bn = (uint32_t)p.block_n;
     const bool skip_mma = p.dbg & 2;
-    const uint32_t idesc_half = make_idesc_bf16(kTileM, SPX ? p.block_n >> 1 : p.block_n);
-    const uint32_t idesc_quarter = make_idesc_bf16(kTileM, SPX ? p.block_n >> 2 : p.block_n);
+    const uint32_t idesc_half = make_idesc_bf16(kTileM, SPX == 1 ? p.block_n >> 1 : p.block_n);
+    const uint32_t idesc_quarter = make_idesc_bf16(kTileM, SPX == 1 ? p.block_n >> 2 : p.block_n);
     if (elect_one()) {
       if (RESIDENT) mbar_wait(bres_bar, 0);
       int sa = 0; uint32_t pha = 0;
@@ -429,8 +435,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               // writes all bn columns, everything after it accumulates.
               auto spx_tap = [&](auto r_c, auto c_c, uint32_t accumulate) {
                 constexpr int R = decltype(r_c)::value, C = decltype(c_c)::value;
-                constexpr int QN = (R == 1) ? 4 : (C == 1 ? 2 : 1);
-                constexpr int QOFF = (R == 1) ? 0 : 2 * (R == 2) + (C == 1 ? 0 : (C == 2));
+                constexpr int QN = (SPX == 2 || R == 1) ? 4 : (C == 1 ? 2 : 1);          // stride-2 mode: always all columns
+                constexpr int QOFF = (SPX == 2 || R == 1) ? 0 : 2 * (R == 2) + (C == 1 ? 0 : (C == 2));
                 constexpr uint32_t shift = (uint32_t)(R * PW + C);
                 const uint32_t a_st = a_lo0_sw + (uint32_t)sa * a_stage_units;
                 const uint32_t idesc_t = QN == 4 ? idesc : (QN == 2 ? idesc_half : idesc_quarter);
@@ -449,7 +455,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                 umma_commit(bempty_bar(sb));
                 if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
               };
-              if (ch < p.split_chunk) {
+              if (SPX == 2) {
+                // stride-2 conv: plane (ph,pw) meets halo rows {1} / {0,1} (ph = 0 / 1), columns likewise
+                const int par = ch / p.spx_cpp;
+                if (par == 0) { spx_tap(I1{}, I1{}, (uint32_t)ch); }
+                else if (par == 1) { spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I1{}, 1u); }
+                else if (par == 2) { spx_tap(I0{}, I1{}, 1u); spx_tap(I1{}, I1{}, 1u); }
+                else { spx_tap(I0{}, I0{}, 1u); spx_tap(I0{}, I1{}, 1u); spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I1{}, 1u); }
+              } else if (ch < p.split_chunk) {
                 spx_tap(I1{}, I1{}, (uint32_t)ch);
                 spx_tap(I0{}, I0{}, 1u); spx_tap(I0{}, I1{}, 1u); spx_tap(I0{}, I2{}, 1u);
                 spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I2{}, 1u);
@@ -467,7 +480,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             else if (p.mix && ch >= p.split_chunk) issue_chunk(std::true_type{}, I0{}, I0{}, IH{}, IW{});  // skip source: TMA box
             else issue_chunk(std::false_type{}, I0{}, I0{}, IH{}, IW{});                                   // upsampled source: gather
           } else if (!RESIDENT) {
-            for (int tap0 = 0; tap0 < ((SPX && ch >= p.split_chunk) ? 4 : NT); tap0 += p.kpb) {
+            const int par2 = (SPX == 2) ? ch / p.spx_cpp : 0;
+            const int nt_ch = (SPX == 2) ? ((par2 >> 1) + 1) * ((par2 & 1) + 1) : ((SPX && ch >= p.split_chunk) ? 4 : NT);
+            for (int tap0 = 0; tap0 < nt_ch; tap0 += p.kpb) {
               mbar_wait_fast(bfull_bar(sb), phb);
               umma_commit(bempty_bar(sb));
               if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }

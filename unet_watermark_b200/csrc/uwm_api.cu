@@ -140,6 +140,7 @@ struct ConvSpec {
   void* out = nullptr;
   long long out_pitch = 0;
   int shuffle = 0;                // sub-pixel conv: real cout; `cout`/`cout_pad` are then 4x that (one group per output parity)
+  int s2planes = 0;               // stride-2 3x3 conv with UWM_PACK_S2_PLANES weights: parity-plane halo kernel (build_halo_s2)
   int s2d = 0;                    // x (and out, or the head's 4 logits per block) are space-to-depth: [n,h,w,4*16], see conv_halo.cuh S2D
   int head = 0, apply_sigmoid = 0;
   float* logits = nullptr;
@@ -304,6 +305,107 @@ static int build_halo_spx(const ConvSpec& s, ConvLaunch* L) {
     if (r != CUDA_SUCCESS)
       return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(sub-pixel skip, element stride 2) -> %d (box %u,%u,%u)", (int)r, abox[0],
                   abox[1], abox[2]);
+  }
+  return UWM_OK;
+}
+
+// Stride-2 3x3 conv (pad 1) on the halo kernel (conv_halo.cuh, SPX == 2): the input's four parity planes arrive as
+// dense TMA boxes (element stride 2), plane (ph,pw) meets the 1, 2, 2 or 4 halo taps that kernel taps (kr,kc) with
+// kr odd/even = ph, kc likewise map to.  s.h, s.w: INPUT size (even); output [n, h/2, w/2, cout].
+//   weights: UWM_PACK_S2_PLANES, [cout][9 * cin] as 64-channel slices in issue order
+static int build_halo_s2(const ConvSpec& s, ConvLaunch* L) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const int kc = 64;
+  if (s.cin % kc || s.cout_pad % 64 || s.cout != s.cout_pad || (s.h & 1) || (s.w & 1) || s.x2 || s.up1 || s.res || s.head)
+    return fail(UWM_EINVAL, "stride-2 plane conv: needs cin%%64 == 0, cout%%64 == 0, even input size, one source, no residual");
+  if ((s.x_pitch * 2) % 16 || (reinterpret_cast<uintptr_t>(s.x) & 15) || (s.out_pitch * 2) % 16 ||
+      (reinterpret_cast<uintptr_t>(s.out) & 15))
+    return fail(UWM_EINVAL, "stride-2 plane conv: activation/output base and pitch must be 16-byte aligned");
+  const int ho = s.h / 2, wo = s.w / 2;
+  const int bn = (s.cout_pad % 128 == 0) ? 128 : 64;
+  const int n_tiles = s.cout_pad / bn;
+  const int sms = num_sms();
+  auto m_tiles_of = [&](int tg) { return ((wo + kHaloTW * tg - 1) / (kHaloTW * tg)) * ((ho + kHaloTH - 1) / kHaloTH) * s.n; };
+  const int tg = (wo >= 2 * kHaloTW && m_tiles_of(2) * n_tiles * 5 >= sms * 4) ? 2 : 1;   // two sub-tiles halve the weight traffic
+  L->halo = 1;
+  HaloKArgs& a = L->hargs;
+  memset(&a, 0, sizeof(a));
+  L->kh = 2; L->kw = 2; L->kc = kc; L->tg = tg; L->resident = 0; L->a_tma = 1; L->spx = 2;
+  a.n_img = s.n; a.h = ho; a.w = wo;
+  a.spx_cpp = s.cin / kc;
+  a.chunks = 4 * a.spx_cpp;
+  a.split_chunk = 0;
+  a.spx_slices = 9 * a.spx_cpp;
+  a.dh_min = -1; a.dw_min = -1;
+  a.cin_total = s.cin;
+  a.tiles_w = (wo + kHaloTW * tg - 1) / (kHaloTW * tg);
+  a.tiles_h = (ho + kHaloTH - 1) / kHaloTH;
+  a.block_n = bn; a.n_tiles = n_tiles; a.cout = s.cout;
+  a.total_tiles = a.tiles_w * a.tiles_h * s.n * n_tiles;
+  a.div_ntiles = make_fastdiv(n_tiles);
+  a.div_tw = make_fastdiv(a.tiles_w);
+  a.div_th = make_fastdiv(a.tiles_h);
+  a.pw_magic = 65536u / (uint32_t)halo_pw(tg, 2) + 1u;
+  const unsigned grid = (unsigned)std::min(a.total_tiles, sms);
+  a.b_slice_bytes = (uint32_t)bn * kc * 2u;
+  a.kpb = 1;
+  const size_t stg_bytes = (size_t)8 * 32 * 128 + 1024;
+  const size_t a_stage_bytes = (((size_t)halo_npix(tg, 2, 2) * kc * 2) + 1023) & ~(size_t)1023;
+  const size_t kBudget = 206u * 1024u - stg_bytes;
+  a.a_stages = 3;
+  a.b_stages = (int)std::min<size_t>(12, (kBudget - a.a_stages * a_stage_bytes) / a.b_slice_bytes);
+  if (a.b_stages < 2) return fail(UWM_ESTATE, "stride-2 plane conv: rings do not fit shared memory");
+  a.nacc_log2 = (4 * tg * bn <= 512) ? 2 : 1;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)((1 << a.nacc_log2) * tg * bn)) cols <<= 1;
+  a.tmem_cols = cols;
+  a.bias = s.bias;
+  a.out = static_cast<__nv_bfloat16*>(s.out);
+  a.out_pitch = s.out_pitch;
+  a.relu = s.relu;
+  a.ep_tma = 1; a.ep_cols = 64;
+  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.trace = g_halo_trace;
+  a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x); a.src[0].pitch = s.x_pitch; a.src[0].h = s.h; a.src[0].w = s.w;
+  a.src[1] = a.src[0];
+  { const char* e = getenv("UWM_VERBOSE");
+    if (e && e[0] == '1')
+      fprintf(stderr, "halo conv (stride-2 planes) %dx%dx%d cin=%d cout=%d: bn=%d tg=%d tiles=%d grid=%u a_stages=%d b_stages=%d slices=%d\n",
+              s.n, s.h, s.w, s.cin, s.cout, bn, tg, a.total_tiles, grid, a.a_stages, a.b_stages, a.spx_slices); }
+  L->grid = grid;
+  L->smem = 1024 + (size_t)a.b_stages * a.b_slice_bytes + (size_t)a.a_stages * a_stage_bytes + stg_bytes + 1024 +
+            (size_t)s.cout_pad * 4;
+
+  const cuuint64_t ktot = (cuuint64_t)9 * s.cin;
+  cuuint64_t dims[2] = {ktot, (cuuint64_t)s.cout_pad};
+  cuuint64_t strides[1] = {ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = enc(&L->tm_wgt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims, strides, box, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(stride-2 wgt) -> %d", (int)r);
+  {
+    cuuint64_t odims[4] = {(cuuint64_t)s.cout, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)s.n};
+    cuuint64_t ostr[3] = {(cuuint64_t)s.out_pitch * 2, (cuuint64_t)wo * s.out_pitch * 2, (cuuint64_t)ho * wo * s.out_pitch * 2};
+    cuuint32_t obox[4] = {64, (cuuint32_t)kHaloTW, 4, 1};
+    cuuint32_t oest[4] = {1, 1, 1, 1};
+    r = enc(&L->tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s.out, odims, ostr, obox, oest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(stride-2 out) -> %d", (int)r);
+    L->tm_res = L->tm_out;
+  }
+  {   // every second pixel of every second row of the input: one parity plane per box
+    cuuint64_t adims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
+    cuuint64_t astr[3] = {(cuuint64_t)s.x_pitch * 2, (cuuint64_t)s.w * s.x_pitch * 2, (cuuint64_t)s.h * s.w * s.x_pitch * 2};
+    cuuint32_t abox[4] = {(cuuint32_t)kc, 2 * (cuuint32_t)halo_pw(tg, 2), 2 * (cuuint32_t)(kHaloTH + 1), 1};
+    cuuint32_t aest[4] = {1, 2, 2, 1};
+    r = enc(&L->tm_a1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.x), adims, astr, abox, aest,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(stride-2 planes) -> %d", (int)r);
+    L->tm_a0 = L->tm_a1;
   }
   return UWM_OK;
 }
@@ -558,6 +660,7 @@ static int build_conv_stream(const ConvSpec& s, ConvLaunch* L);
 // Kernel selection: k x k stride-1 'same' convs (and anything with a fused upsample/concat) go to the
 // halo-resident kernel; stride-2 and 1x1 convs (plain GEMM, nothing to share between taps) to conv_tc.
 static int build_conv(const ConvSpec& s, ConvLaunch* L) {
+  if (s.s2planes) return build_halo_s2(s, L);
   const bool fused = s.up1 || s.x2;
   const bool same = (s.stride == 1 && s.h_out == s.h && s.w_out == s.w);
   if (fused || (same && (s.ntaps == 9 || s.ntaps == 16) && halo_enabled())) return build_halo(s, L);
@@ -708,10 +811,10 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   // space-to-depth 3x3 convs (S2D): one 64-channel chunk = 4 parity planes x 16, resident weights, TMA-fed
 #define UWM_HALO_S2D(TG)                                                                                          \
   if (!L) {                                                                                                       \
-    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, true, true, false, true>,                        \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, true, true, 0, true>,                            \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
   } else if (L->s2d && L->tg == TG && L->kc == 64 && L->resident && L->a_tma) {                                   \
-    launch_pdl(conv_halo_kernel<64, 3, 3, TG, true, true, false, true>, L->grid, kHaloThreads, L->smem, st,       \
+    launch_pdl(conv_halo_kernel<64, 3, 3, TG, true, true, 0, true>, L->grid, kHaloThreads, L->smem, st,           \
                L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                    \
     return UWM_OK;                                                                                                \
   }
@@ -721,15 +824,27 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   // sub-pixel upcat conv (SPX): 64-channel chunks, streamed weights, TMA-fed
 #define UWM_HALO_SPX(TG)                                                                                          \
   if (!L) {                                                                                                       \
-    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, false, true, true>,                              \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, false, true, 1>,                                 \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
-  } else if (L->spx && L->tg == TG) {                                                                             \
-    launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, true>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,  \
+  } else if (L->spx == 1 && L->tg == TG) {                                                                             \
+    launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, 1>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,     \
                L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
     return UWM_OK;                                                                                                \
   }
   UWM_HALO_SPX(1) UWM_HALO_SPX(2)
 #undef UWM_HALO_SPX
+  // stride-2 3x3 convs over parity planes (SPX == 2): 2x2 block halo
+#define UWM_HALO_S2(TG)                                                                                           \
+  if (!L) {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 2, 2, TG, false, true, 2>,                                 \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
+  } else if (L->spx == 2 && L->tg == TG) {                                                                        \
+    launch_pdl(conv_halo_kernel<64, 2, 2, TG, false, true, 2>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,     \
+               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
+    return UWM_OK;                                                                                                \
+  }
+  UWM_HALO_S2(1) UWM_HALO_S2(2)
+#undef UWM_HALO_S2
   if (!L) return UWM_OK;
   return fail(UWM_ESTATE, "halo conv: no kernel instantiated for kc=%d %dx%d tg=%d resident=%d a_tma=%d", L->kc, L->kh,
               L->kw, L->tg, L->resident, L->a_tma);
@@ -873,6 +988,22 @@ extern "C" int uwm_head_nhwc_bf16(const void* d_x, int n, int h, int w, int cin,
   return launch_conv(L, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int uwm_conv2d_s2_planes_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                              const void* d_wgt, const float* d_bias, int cout, int relu, void* d_y,
+                                              int y_pitch, void* stream) {
+  if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_s2_planes: null pointer");
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = cin; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = cout; s.cout_pad = cout; s.s2planes = 1;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 2; s.h_out = h / 2; s.w_out = w / 2;
+  s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_halo_s2(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int uwm_conv2d_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int x_pitch, const void* d_wgt,
                                         const float* d_bias, int relu, void* d_y, int y_pitch, void* stream) {
   if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_s2d: null pointer");
@@ -978,6 +1109,7 @@ struct Layer {
   uwm_layer_desc d;
   bool stem = false;
   bool shuffle = false;    // decoder conv1 without a skip: 3x3 conv on the upsampled input as a sub-pixel conv
+  bool s2planes = false;   // stride-2 3x3 conv on the parity-plane halo kernel (UWM_PACK_S2_PLANES)
   bool s2d = false;        // 3x3 conv over a space-to-depth tensor (conv_halo.cuh S2D); d.cin/d.cout stay the reference's
   void* d_w = nullptr;
   float* d_b = nullptr;
@@ -1074,7 +1206,10 @@ static int add_layer(uwm_model* m, const std::string& conv_key, const std::strin
     L.d.cout_pad = 4 * cout;                       // GEMM N; cout must be a multiple of 16 (checked at create)
     L.d.w_elems = (int64_t)L.d.cout_pad * 9 * cin;
   } else {
-    L.d.pack = UWM_PACK_TAPS;
+    // stride-2 3x3 convs whose channels split into 64-wide chunks run on the parity-plane halo kernel
+    static const bool s2_on = []{ const char* e = getenv("UWM_S2PLANES"); return !(e && e[0] == '0'); }();
+    L.s2planes = s2_on && halo_enabled() && k == 3 && stride == 2 && pad == 1 && cin % 64 == 0 && cout % 64 == 0 && !has_res;
+    L.d.pack = L.s2planes ? UWM_PACK_S2_PLANES : UWM_PACK_TAPS;
     L.d.w_elems = (int64_t)L.d.cout_pad * k * k * cin;
   }
   L.d.b_elems = L.d.cout_pad;
@@ -1357,6 +1492,7 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
           s.h_out = op.in.h; s.w_out = op.in.w;
         } else {
           s.cin = op.in.c; s.stride = ly.d.stride;
+          if (ly.s2planes) s.s2planes = 1;     // input sizes are even (H, W divisible by 32)
           if (ly.s2d) { s.s2d = 1; if (op.type != OP_HEAD) s.cout = ly.d.cout_pad; }
           if (ly.shuffle) {   // runs on the source grid, N = 4*cout; a space-to-depth output keeps the GEMM layout
             s.cout = ly.d.cout_pad;

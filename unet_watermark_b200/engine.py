@@ -76,6 +76,9 @@ class Engine:
             if d.pack == _lib.PACK_STEM_S2D:
                 wp = packing.pack_stem_s2d(w, d.cout_pad)
                 bp = packing.pad_bias(b, d.cout_pad)
+            elif d.pack == _lib.PACK_S2_PLANES:
+                wp = packing.pack_s2_planes(w)                              # stride-2 conv over parity planes
+                bp = packing.pad_bias(b, d.cout_pad)
             elif d.pack == _lib.PACK_S2D_CONV:
                 wp = packing.pack_s2d_conv3x3(w, d.cout_pad)               # conv on a space-to-depth tensor
                 bp = packing.pad_bias(b, d.cout_pad) if d.cout == 1 else b.detach().float().repeat(4).contiguous()

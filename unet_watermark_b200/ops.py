@@ -128,6 +128,22 @@ def head(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, threshold:
     return logits, mask
 
 
+def conv2d_s2_planes(x: torch.Tensor, w_planes: torch.Tensor, bias: torch.Tensor, relu: bool = True,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stride-2 conv3x3 (pad 1) on the parity-plane halo kernel.  x: [N,h,w,Cin] (h, w even, Cin % 64 == 0);
+    w_planes: packing.pack_s2_planes(w) = [Cout, 9*Cin] bf16 (Cout % 64 == 0)."""
+    _require_cuda(x, w_planes, bias, out)
+    lib = _lib.load()
+    n, h, w, cin = x.shape
+    cout = w_planes.shape[0]
+    if out is None:
+        out = torch.empty(n, h // 2, w // 2, cout, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_s2_planes_nhwc_bf16(x.data_ptr(), n, h, w, cin, _pitch(x), w_planes.data_ptr(), bias.data_ptr(),
+                                            cout, int(relu), out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_s2_planes_nhwc_bf16")
+    return out
+
+
 def conv2d_s2d(x: torch.Tensor, w_s2d: torch.Tensor, bias4: torch.Tensor, relu: bool = True,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """conv3x3 'same' on a 16-channel tensor kept space-to-depth: x, out = [N,h,w,64] standing for [N,2h,2w,16].

@@ -116,6 +116,28 @@ def pack_upcat_subpixel(w: torch.Tensor, c_x: int) -> torch.Tensor:
     return torch.cat(slices, dim=1).to(torch.bfloat16).contiguous()
 
 
+def pack_s2_planes(w: torch.Tensor) -> torch.Tensor:
+    """Stride-2 3x3 conv (pad 1) as stride-1 taps on the input's four parity planes (UWM_PACK_S2_PLANES).
+
+    Output pixel (i,j) reads input row 2i+kr-1: kr = 1 is (block i, plane 0), kr = 0 / 2 are (block i-1 / i, plane 1).
+    With a 2x2 block halo at origin -1 (halo row r = 0 is block i-1, r = 1 block i) plane ph meets rows {1} (ph = 0)
+    or {0, 1} (ph = 1); columns likewise.  Returns bf16 [Cout, 9*Cin]: 64-channel slices in issue order - plane
+    (ph,pw) major, then 64-channel chunk, then taps (r,c) row-major."""
+    cout, cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3) and cin % 64 == 0
+    wb = w.detach().float()
+    slices = []
+    for ph in range(2):
+        for pw in range(2):
+            for cc in range(cin // 64):
+                for r in ((1,) if ph == 0 else (0, 1)):
+                    kr = 1 if ph == 0 else (0 if r == 0 else 2)
+                    for c in ((1,) if pw == 0 else (0, 1)):
+                        kcol = 1 if pw == 0 else (0 if c == 0 else 2)
+                        slices.append(wb[:, cc * 64:(cc + 1) * 64, kr, kcol])
+    return torch.cat(slices, dim=1).to(torch.bfloat16).contiguous()
+
+
 def pack_s2d_conv3x3(w: torch.Tensor, rows: int = 0) -> torch.Tensor:
     """conv3x3 on a tensor stored space-to-depth (UWM_PACK_S2D_CONV).
 
