@@ -101,6 +101,7 @@ struct HaloKArgs {
   float* logits;
   uint8_t* mask;
   float thr_logit;
+  int a_scale;                              // A_TMA loaders: box start = a_scale * tile origin (2: the map walks every second pixel)
   int spx_cpp, spx_slices;                  // SPX kernels: 64-channel chunks per parity plane of src[1]; weight slices per tile
   int mix;                                  // !A_TMA kernels: chunks of src[1] arrive as TMA boxes (swizzled stage layout)
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
@@ -742,7 +743,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             if (!(p.dbg & 1)) {
               mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
               if (ch < p.split_chunk)
-                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase, hbase, t.img);
+                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase * p.a_scale,
+                            hbase * p.a_scale, t.img);
               else if (SPX) {
                 // parity plane (ph,pw) of the full-resolution skip source: halo block b is pixel 2b + parity
                 const int e = ch - p.split_chunk, par = e / p.spx_cpp, cc = e - par * p.spx_cpp;

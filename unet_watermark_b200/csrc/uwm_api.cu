@@ -140,6 +140,7 @@ struct ConvSpec {
   void* out = nullptr;
   long long out_pitch = 0;
   int shuffle = 0;                // sub-pixel conv: real cout; `cout`/`cout_pad` are then 4x that (one group per output parity)
+  int in_stride2 = 0, h_in = 0, w_in = 0;   // 1x1 stride-2 conv as a stride-1 conv on every second pixel of a [h_in, w_in] source
   int s2planes = 0;               // stride-2 3x3 conv with UWM_PACK_S2_PLANES weights: parity-plane halo kernel (build_halo_s2)
   int s2d = 0;                    // x (and out, or the head's 4 logits per block) are space-to-depth: [n,h,w,4*16], see conv_halo.cuh S2D
   int head = 0, apply_sigmoid = 0;
@@ -223,6 +224,7 @@ static int build_halo_spx(const ConvSpec& s, ConvLaunch* L) {
   a.spx_cpp = s.cin2 / kc;
   a.spx_slices = 9 * (s.cin / kc) + 16 * (s.cin2 / kc);
   a.dh_min = -1; a.dw_min = -1;
+  a.a_scale = 1;
   a.cin_total = s.cin + s.cin2;
   a.tiles_w = (s.w + kHaloTW * tg - 1) / (kHaloTW * tg);
   a.tiles_h = (s.h + kHaloTH - 1) / kHaloTH;
@@ -338,6 +340,7 @@ static int build_halo_s2(const ConvSpec& s, ConvLaunch* L) {
   a.split_chunk = 0;
   a.spx_slices = 9 * a.spx_cpp;
   a.dh_min = -1; a.dw_min = -1;
+  a.a_scale = 1;
   a.cin_total = s.cin;
   a.tiles_w = (wo + kHaloTW * tg - 1) / (kHaloTW * tg);
   a.tiles_h = (ho + kHaloTH - 1) / kHaloTH;
@@ -457,6 +460,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   if (!((kh == 3 && kw == 3) || (kh == 1 && kw == 1) || (kh == 4 && kw == 4 && kc == 16)))
     return fail(UWM_EINVAL, "halo conv: %dx%d filters with %d-channel chunks are not instantiated", kh, kw, kc);
   a.dh_min = dh_min; a.dw_min = dw_min;
+  a.a_scale = s.in_stride2 ? 2 : 1;
   a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x);
   a.src[0].pitch = s.x_pitch; a.src[0].up = s.up1 ? 1 : 0;
   a.src[0].h = s.up1 ? s.h / 2 : s.h; a.src[0].w = s.up1 ? s.w / 2 : s.w;
@@ -641,10 +645,12 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const void* base = i ? s.x2 : s.x;
       const long long pitch = i ? s.x2_pitch : s.x_pitch;
       const int csrc = i ? s.cin2 : s.cin;
-      cuuint64_t adims[4] = {(cuuint64_t)csrc, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
-      cuuint64_t astr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)s.w * pitch * 2, (cuuint64_t)s.h * s.w * pitch * 2};
-      cuuint32_t abox[4] = {(cuuint32_t)kc, (cuuint32_t)halo_pw(tg, kw), (cuuint32_t)(kHaloTH + kh - 1), 1};
-      cuuint32_t aest[4] = {1, 1, 1, 1};
+      const int sc = s.in_stride2 ? 2 : 1;          // strided view: the box spans 2x the pixels, every second one lands
+      const int hs = s.in_stride2 ? s.h_in : s.h, ws = s.in_stride2 ? s.w_in : s.w;
+      cuuint64_t adims[4] = {(cuuint64_t)csrc, (cuuint64_t)ws, (cuuint64_t)hs, (cuuint64_t)s.n};
+      cuuint64_t astr[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)ws * pitch * 2, (cuuint64_t)hs * ws * pitch * 2};
+      cuuint32_t abox[4] = {(cuuint32_t)kc, (cuuint32_t)(sc * halo_pw(tg, kw)), (cuuint32_t)(sc * (kHaloTH + kh - 1)), 1};
+      cuuint32_t aest[4] = {1, (cuuint32_t)sc, (cuuint32_t)sc, 1};
       r = enc(i ? &L->tm_a1 : &L->tm_a0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), adims, astr, abox,
               aest, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS)
@@ -667,6 +673,15 @@ static int build_conv(const ConvSpec& s, ConvLaunch* L) {
   // 1x1 stride-1: TMA-fed halo kernel (no halo, but TMA stores and the two epilogue sets) when cin is a multiple of 64
   static const bool pw_halo = []{ const char* e = getenv("UWM_PW_HALO"); return !(e && e[0] == '0'); }();
   if (same && s.ntaps == 1 && s.cin % 64 == 0 && halo_enabled() && pw_halo) return build_halo(s, L);
+  // 1x1 stride-2 (ResNet downsample): the same kernel on a TMA view of every second pixel
+  static const bool ds_halo = []{ const char* e = getenv("UWM_DS_HALO"); return !(e && e[0] == '0'); }();
+  if (s.stride == 2 && s.ntaps == 1 && s.dh[0] == 0 && s.dw[0] == 0 && s.cin % 64 == 0 && s.cout_pad % 64 == 0 &&
+      !(s.h & 1) && !(s.w & 1) && halo_enabled() && pw_halo && ds_halo) {
+    ConvSpec v = s;
+    v.in_stride2 = 1; v.h_in = s.h; v.w_in = s.w;
+    v.stride = 1; v.h = s.h_out; v.w = s.w_out;
+    return build_halo(v, L);
+  }
   return build_conv_stream(s, L);
 }
 
