@@ -356,7 +356,8 @@ static int build_halo_s2(const ConvSpec& s, ConvLaunch* L) {
   const size_t stg_bytes = (size_t)8 * 32 * 128 + 1024;
   const size_t a_stage_bytes = (((size_t)halo_npix(tg, 2, 2) * kc * 2) + 1023) & ~(size_t)1023;
   const size_t kBudget = 206u * 1024u - stg_bytes;
-  a.a_stages = 3;
+  // a plane stage lasts 1-4 taps x 4 K-steps; weight slices turn over every ~512 cycles and must cover the L2 latency
+  a.a_stages = (tg == 2) ? 2 : 3;
   a.b_stages = (int)std::min<size_t>(12, (kBudget - a.a_stages * a_stage_bytes) / a.b_slice_bytes);
   if (a.b_stages < 2) return fail(UWM_ESTATE, "stride-2 plane conv: rings do not fit shared memory");
   a.nacc_log2 = (4 * tg * bn <= 512) ? 2 : 1;
@@ -521,8 +522,9 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const double a_bytes = (double)halo_npix(tg, kh, kw) * cin_total * 2;
       const double b_bytes = resident ? 0.0 : (double)bn * nk * kc * 2;
       const int a_stages_fit = (int)((kBudget - (resident ? (size_t)nk * b_slice : 2 * b_slice)) / a_stage);
-      const double shallow = a_stages_fit < 3 ? 1.25 : 1.0;        // two stages cannot hide the load latency
-      const double t_sm = waves * std::max(std::max(tensor, issue), (a_bytes + b_bytes) / 64.0) * shallow;
+      const double shallow = a_stages_fit < 3 ? 1.08 : 1.0;        // two stages hide the load latency a little less well (measured)
+      // + ~450 cycles per tile of barrier hand-offs that nothing overlaps (trace: 2220-cycle cadence on 1764 cycles of MMAs)
+      const double t_sm = waves * (std::max(std::max(tensor, issue), (a_bytes + b_bytes) / 64.0) * shallow + 450.0);
       const double t_l2 = tiles * (a_bytes + b_bytes) / 6300.0;
       const double cost = std::max(t_sm, t_l2);
       if (cost < best.cost * 0.97) best = {bn, tg, resident, cost};
