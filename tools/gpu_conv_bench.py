@@ -11,6 +11,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("UWM_OP_PDL", "1")   # time single ops with programmatic dependent launch, as the plan runs them
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from unet_watermark_b200 import ops, packing  # noqa: E402
 

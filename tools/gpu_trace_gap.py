@@ -12,6 +12,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("UWM_OP_PDL", "1")   # time single ops with programmatic dependent launch, as the plan runs them
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tools.gpu_conv_bench import SHAPES  # noqa: E402
 from unet_watermark_b200 import _lib, ops, packing  # noqa: E402

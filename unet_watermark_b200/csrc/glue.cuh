@@ -27,11 +27,61 @@ __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ 
                                                        __nv_bfloat16* __restrict__ out, int n,
                                                        int h, int w) {
   pdl_launch_dependents();
+  // u8: 256 possible inputs per channel - the normalisation is tabulated once per block with the reference's fp32
+  // operation order ((x/255 - mean)/std, true division) and rounded to bf16 exactly as the per-element path would
+  __shared__ __nv_bfloat16 lut[3][256];
+  if (kU8) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int k = threadIdx.x; k < 768; k += blockDim.x) {
+      const int c = k >> 8;
+      lut[c][k & 255] = __float2bfloat16_rn(((float)(k & 255) * (1.0f / 255.0f) - mean[c]) / stdv[c]);
+    }
+    __syncthreads();
+  }
   pdl_wait();
   const int h2 = h >> 1, w2 = w >> 1;
+  if (kU8 && (w & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
+    // two output pixels per thread: 4 input pixels = 12 bytes = three aligned 32-bit loads per input row
+    const int w4 = w >> 2;
+    const long long total = (long long)n * h2 * w4;
+    const uint8_t* src = static_cast<const uint8_t*>(in);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+      const int jj = (int)(idx % w4);
+      const int i = (int)((idx / w4) % h2);
+      const int b = (int)(idx / ((long long)w4 * h2));
+      uint16_t v[2][16];                         // [output pixel][channel (ph*2+pw)*3 + c], bf16 bits
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 12; k < 16; ++k) v[o][k] = 0;
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (((long long)b * h + (2 * i + ph)) * w + 4 * jj) * 3);
+        const uint32_t q[3] = {__ldg(r), __ldg(r + 1), __ldg(r + 2)};
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {           // byte e = pixel e/3 (0..3), channel e%3
+          const uint32_t byte = (q[e >> 2] >> (8 * (e & 3))) & 0xffu;
+          const int px = e / 3, c = e - 3 * px;
+          v[px >> 1][(ph * 2 + (px & 1)) * 3 + c] = __bfloat16_as_ushort(lut[c][byte]);
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * h2 + i) * w2 + 2 * jj) * 16);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        uint4 o0, o1;
+        o0.x = v[o][0] | ((uint32_t)v[o][1] << 16);   o0.y = v[o][2] | ((uint32_t)v[o][3] << 16);
+        o0.z = v[o][4] | ((uint32_t)v[o][5] << 16);   o0.w = v[o][6] | ((uint32_t)v[o][7] << 16);
+        o1.x = v[o][8] | ((uint32_t)v[o][9] << 16);   o1.y = v[o][10] | ((uint32_t)v[o][11] << 16);
+        o1.z = 0; o1.w = 0;
+        dst[2 * o] = o0;
+        dst[2 * o + 1] = o1;
+      }
+    }
+    return;
+  }
   const long long total = (long long)n * h2 * w2;
-  const float mean[3] = {0.485f, 0.456f, 0.406f};
-  const float stdv[3] = {0.229f, 0.224f, 0.225f};
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % w2);
@@ -49,11 +99,7 @@ __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ 
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            // same operation order as albumentations Normalize: (x/255 - mean)/std, in fp32
-            const float x = (float)r[pw * 3 + c];
-            v[(ph * 2 + pw) * 3 + c] = (x * (1.0f / 255.0f) - mean[c]) / stdv[c];
-          }
+          for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = __bfloat162float(lut[c][r[pw * 3 + c]]);
       }
     } else {
       const float* src = static_cast<const float*>(in);
@@ -92,6 +138,7 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 // MaxPool2d(kernel 3, stride 2, padding 1), NHWC bf16.  Padding is -inf (PyTorch semantics):
 // out-of-range taps are skipped.  One thread per (output pixel, 8-channel group).
 // ---------------------------------------------------------------------------------------------
+constexpr int kPoolRows = 8;     // output rows per thread: input row 2i+1 is shared by outputs i and i+1, kept in registers
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x,
                                                            __nv_bfloat16* __restrict__ y, int n,
                                                            int h, int w, int c, long long x_pitch,
@@ -99,31 +146,36 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
   pdl_launch_dependents();
   pdl_wait();
   const int ho = h >> 1, wo = w >> 1, cg = c >> 3;
-  const long long total = (long long)n * ho * wo * cg;
+  const int strips = (ho + kPoolRows - 1) / kPoolRows;
+  const long long total = (long long)n * strips * wo * cg;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
+    // a warp = 4 adjacent output columns x 8 channel groups: every load instruction covers whole 128-byte lines, and
+    // the column 2j+1 shared with the neighbouring output is an L1 hit
     const int g = (int)(idx % cg);
     long long t = idx / cg;
     const int j = (int)(t % wo); t /= wo;
-    const int i = (int)(t % ho);
-    const int b = (int)(t / ho);
-    uint4 m;
-    bool first = true;
-#pragma unroll
-    for (int dh = -1; dh <= 1; ++dh) {
-      const int ih = 2 * i + dh;
-      if (ih < 0 || ih >= h) continue;
-#pragma unroll
-      for (int dw = -1; dw <= 1; ++dw) {
-        const int iw = 2 * j + dw;
-        if (iw < 0 || iw >= w) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(
-            x + (((long long)b * h + ih) * w + iw) * x_pitch + g * 8);
-        m = first ? v : hmax8(m, v);
-        first = false;
-      }
+    const int i0 = (int)(t % strips) * kPoolRows;
+    const int b = (int)(t / strips);
+    const __nv_bfloat16* img = x + (long long)b * h * w * x_pitch + g * 8;
+    auto row_max = [&](int ih) {           // max over columns 2j-1 .. 2j+1 of input row ih (ih in range)
+      const __nv_bfloat16* r = img + ((long long)ih * w + 2 * j) * x_pitch;
+      uint4 m = hmax8(*reinterpret_cast<const uint4*>(r), *reinterpret_cast<const uint4*>(r + x_pitch));   // 2j+1 < w: w even
+      if (j > 0) m = hmax8(m, *reinterpret_cast<const uint4*>(r - x_pitch));
+      return m;
+    };
+    uint4 prev = make_uint4(0, 0, 0, 0);
+    bool have_prev = i0 > 0;
+    if (have_prev) prev = row_max(2 * i0 - 1);
+#pragma unroll 2
+    for (int i = i0; i < min(i0 + kPoolRows, ho); ++i) {
+      const uint4 a = row_max(2 * i);
+      const uint4 bb = row_max(2 * i + 1);                // 2i+1 < h: h even
+      uint4 m = hmax8(a, bb);
+      if (have_prev) m = hmax8(m, prev);
+      prev = bb; have_prev = true;
+      *reinterpret_cast<uint4*>(y + (((long long)b * ho + i) * wo + j) * y_pitch + g * 8) = m;
     }
-    *reinterpret_cast<uint4*>(y + (((long long)b * ho + i) * wo + j) * y_pitch + g * 8) = m;
   }
 }
 

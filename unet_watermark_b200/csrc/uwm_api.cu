@@ -95,6 +95,12 @@ static bool pdl_enabled() {
   if (v < 0) { const char* e = getenv("UWM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+// Programmatic dependent launch lets a kernel start (prologue, weight and bias loads) before the previous kernel in the
+// stream has finished; only activation reads / output writes sit behind griddepcontrol.wait.  That is sound inside a
+// model plan, whose weights were uploaded long before.  The single-operator entry points keep plain stream order: a
+// caller may have produced the weights or the bias on this stream one kernel earlier.
+static thread_local int g_plan_depth = 0;
+struct PlanScope { PlanScope() { ++g_plan_depth; } ~PlanScope() { --g_plan_depth; } };
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -102,7 +108,8 @@ static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  static const bool op_pdl = []{ const char* e = getenv("UWM_OP_PDL"); return e && e[0] == '1'; }();   // bench tools: time single ops as the plan runs them
+  cfg.attrs = attr; cfg.numAttrs = (pdl_enabled() && (g_plan_depth > 0 || op_pdl)) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -1055,7 +1062,7 @@ extern "C" int uwm_head_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int 
 static int launch_maxpool(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
                           cudaStream_t st) {
   if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
-  const long long items = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  const long long items = (long long)n * ((h / 2 + kPoolRows - 1) / kPoolRows) * (w / 2) * (c / 8);
   launch_pdl(maxpool3x3s2_kernel, stream_grid(items, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(x),
              static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
   return post_launch("maxpool3x3s2_kernel", st);
@@ -1073,7 +1080,7 @@ static int launch_prep(const void* in, int fmt, int n, int h, int w, void* y, cu
   const long long items = (long long)n * (h / 2) * (w / 2);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y);
   if (fmt == UWM_IN_U8_NHWC)
-    launch_pdl(prep_s2d_kernel<true>, stream_grid(items, 256), 256, 0, st, in, out, n, h, w);
+    launch_pdl(prep_s2d_kernel<true>, stream_grid((w % 4 == 0) ? items / 2 : items, 256), 256, 0, st, in, out, n, h, w);
   else if (fmt == UWM_IN_F32_NCHW)
     launch_pdl(prep_s2d_kernel<false>, stream_grid(items, 256), 256, 0, st, in, out, n, h, w);
   else
@@ -1545,6 +1552,7 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
 }
 
 static int run_launch(const Launch& L, cudaStream_t st) {
+  PlanScope in_plan;
   switch (L.type) {
     case OP_PREP: return launch_prep(L.src, L.c, L.n, L.h, L.w, L.dst, st);
     case OP_POOL: return launch_maxpool(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
