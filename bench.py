@@ -12,9 +12,9 @@ scaling, no collective on the data path.  Prints ONE JSON line 
   value     images/s, whole job, inputs already resident in HBM (uint8 NHWC), CUDA-event timed
   e2e       images/s through the public API (Unet.predict_mask) from pinned HOST uint8 batches:
             H2D copy + forward + D2H read of the uint8 masks inside the timed region
-  roofline  the tcgen05 implicit-GEMM conv kernels (conv_halo_kernel for the stride-1 3x3 / stem convs,
-            conv_tc_kernel for the stride-2 and 1x1 convs; all conv launches of a step): algorithmic conv
-            FLOPs / summed per-launch CUDA-event time, vs the measured bf16 peak
+  roofline  the tcgen05 implicit-GEMM conv kernel (conv_halo_kernel, every conv launch of a step; conv_tc_kernel
+            only serves shapes it does not cover): algorithmic conv FLOPs / (timed step x live conv share),
+            vs the measured bf16 peak
   cpu_baseline / --impl reference
             the oracle restatement of the reference's CPU path (torch fp32, all host threads) on a
             bounded sample of the same workload.
@@ -287,7 +287,7 @@ def run_ours(args):
                 traffic = json.load(f).get("conv_dram_bytes_per_step")
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs)",
+    roofline = {"bound": "tensor", "kernel": "conv_halo_kernel (tcgen05 implicit-GEMM convs, all conv launches of the step)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
                 "peak_source": peaks["source"] + ", burst figure",

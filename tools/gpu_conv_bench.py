@@ -30,6 +30,8 @@ SHAPES = [  # name, n, h, w, cin (x), cskip, cout, upsample
     ("dec3 32->32 @256", 16, 256, 256, 32, 0, 32, False),
     ("dec4 up32->16 @512", 16, 256, 256, 32, 0, 16, True),
     ("dec4 16->16 @512", 16, 512, 512, 16, 0, 16, False),
+    ("dec4 s2d 16->16 @512", 16, 256, 256, 64, 0, 16, "s2d"),      # h, w, cx in space-to-depth terms
+    ("head s2d 16->1 @512", 16, 256, 256, 64, 0, 1, "s2dhead"),
 ]
 
 
@@ -49,14 +51,25 @@ def main():
         ho, wo = (2 * h, 2 * w) if up else (h, w)
         skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
         cin = cx + cs
-        wt = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
-        wp = packing.pack_upcat_subpixel(wt, cx) if up == "spx" else packing.pack_taps(wt)
-        b = torch.zeros(4 * cout if up == "spx" else cout, device=dev)
-        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+        if up in ("s2d", "s2dhead"):
+            ho, wo, cin = h, w, 16
+            wt = torch.randn(cout, 16, 3, 3, device=dev) / 12
+            wp = packing.pack_s2d_conv3x3(wt, 16 if cout == 1 else 0)
+            b = torch.zeros(16 if cout == 1 else 4 * cout, device=dev)
+            out = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=dev)
+        else:
+            wt = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+            wp = packing.pack_upcat_subpixel(wt, cx) if up == "spx" else packing.pack_taps(wt)
+            b = torch.zeros(4 * cout if up == "spx" else cout, device=dev)
+            out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
         times = []
 
         def run():
-            if up == "spx":
+            if up == "s2d":
+                ops.conv2d_s2d(x, wp, b, relu=True, out=out)
+            elif up == "s2dhead":
+                ops.head_s2d(x, wp, b, threshold=0.5, want_logits=False)
+            elif up == "spx":
                 ops.conv2d_upcat_subpixel(x, skip, wp, b, relu=True, out=out)
             else:
                 ops.conv2d_upcat(x, skip, wp, b, relu=True, upsample=up, out=out)
@@ -86,8 +99,10 @@ def main():
                 torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1) / 10)
         os.environ["UWM_DBG"] = "0"
-        fl = 2.0 * n * ho * wo * cin * cout * 9
+        fl = 2.0 * n * ho * wo * cin * cout * 9 * (4 if up in ("s2d", "s2dhead") else 1)
         by = 2.0 * (x.numel() + out.numel() + (skip.numel() if skip is not None else 0))
+        if up == "s2dhead":
+            by = 2.0 * x.numel() + 4.0 * n * h * w
         ms = times[0]
         print(f"{name:<28s}" + "".join(f"  {t * 1e3:9.1f}" for t in times) +
               f"   {fl / ms / 1e9:8.1f}   {by / ms / 1e6:8.1f}", flush=True)

@@ -29,15 +29,26 @@ def main():
         ho, wo = (2 * h, 2 * w) if up else (h, w)
         skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
         cin = cx + cs
-        wt = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
-        wp = packing.pack_upcat_subpixel(wt, cx) if up == "spx" else packing.pack_taps(wt)
-        b = torch.zeros(4 * cout if up == "spx" else cout, device=dev)
+        wt = torch.randn(cout, 16 if str(up).startswith("s2d") else cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+        if str(up).startswith("s2d"):
+            wp = packing.pack_s2d_conv3x3(wt, 16 if cout == 1 else 0)
+            b = torch.zeros(16 if cout == 1 else 4 * cout, device=dev)
+            ho, wo = h, w
+        else:
+            wp = packing.pack_upcat_subpixel(wt, cx) if up == "spx" else packing.pack_taps(wt)
+            b = torch.zeros(4 * cout if up == "spx" else cout, device=dev)
         out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
         res = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16) if args.residual else None
+
+        s2d_out = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=dev) if up == "s2d" else None
 
         def run():
             if res is not None and not up and skip is None:
                 ops.conv2d(x, wp, b, 3, 3, 1, 1, relu=True, residual=res, out=out)
+            elif up == "s2d":
+                ops.conv2d_s2d(x, wp, b, relu=True, out=s2d_out)
+            elif up == "s2dhead":
+                ops.head_s2d(x, wp, b, threshold=0.5, want_logits=False)
             elif up == "spx":
                 ops.conv2d_upcat_subpixel(x, skip, wp, b, relu=True, out=out)
             else:
