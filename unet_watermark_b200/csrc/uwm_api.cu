@@ -519,6 +519,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const bool resident = (n_tiles == 1) && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
       if (!resident && (tg > 2 || 2 * b_slice + 2 * a_stage > kBudget)) break;   // streamed kernels: TG 1, 2
       if (s.s2d && (!resident || tg > 4 || !a_tma)) break;         // S2D: resident weights, TG 1, 2, 4, TMA-fed
+      if (s.s2d && s.head && tg > 2) break;                        // head: 79 KB stages at TG 4 leave a 2-deep ring (measured slower)
       if (kh == 4 && !resident) break;
       if (kh == 1 && (tg > 4 || !a_tma)) break;                    // 1x1: TG 1, 2, 4, TMA-fed only
       const long long tiles = (long long)((s.w + kHaloTW * tg - 1) / (kHaloTW * tg)) * ((s.h + kHaloTH - 1) / kHaloTH) * s.n * n_tiles;
@@ -1611,9 +1612,11 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
     if (rc) return rc;
     cudaGraph_t g = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed));
-    // The downsample conv of a residual stage reads only the block input: it is captured on a forked stream so the
-    // graph runs it beside the block's first conv, and joined before the conv that adds it as the residual.
-    static const bool fork_side = []{ const char* e = getenv("UWM_FORK"); return !(e && e[0] == '0'); }();
+    // The downsample conv of a residual stage reads only the block input, so it can be captured on a forked stream
+    // beside the block's first conv and joined before the conv that adds it as the residual (UWM_FORK=1).  That paid
+    // while the downsample took 12-22 us on conv_tc_kernel; at ~10 us on the halo kernel the fork/join edges (which
+    // also break the programmatic-launch chain) cost more than the overlap gives, so the default is one stream.
+    static const bool fork_side = []{ const char* e = getenv("UWM_FORK"); return e && e[0] == '1'; }();
     bool pending_join = false;
     for (size_t i = 0; i < n; ++i) {
       const Launch& L = pl.launches[i];
