@@ -127,10 +127,12 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // tcgen05.mma with separate descriptor halves; ACC: accumulate into D unconditionally, else only when acc != 0
-template <bool ACC>
+template <bool ACC, bool CG2 = false>
 __device__ __forceinline__ void umma_halo(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                           uint32_t idesc, uint32_t acc) {
-  if (ACC) {
+  if (CG2) {
+    umma_bf16_lohi2_cg2(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, ACC ? 1u : acc);
+  } else if (ACC) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -191,13 +193,23 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 // with a 2x2 block halo at origin -1 plane ph meets halo rows {1} (ph = 0) or {0,1} (ph = 1): 9 (plane, tap) pairs,
 // one per kernel tap, each a full-N MMA group over a dense TMA-written stage - the stride never reaches the MMA.
 //
+// CG2 (CTA pair, streamed weights): the two CTAs of a 2-CTA cluster work on two M tiles of the same N tile and share
+// every weight slice - each loads HALF of its rows (block_n/2) and the leader issues one M = 256 tcgen05.mma.cta_group::2
+// per tap / K step that reads A from both CTAs' stages (same offsets: the rings run in lockstep), B half from each, and
+// writes each CTA's 128 x N accumulator into its own TMEM.  Per CTA that halves the weight bytes through the L2->SM
+// fabric and through the shared-memory write port (the two things that bound layer4 and slow the MMAs of layer2/3).
+// Protocol: 'full' barriers and the accumulator-free barriers live in the leader: its producers arm them with the
+// bytes of both CTAs and both CTAs' TMA loads complete on them; the accumulator-free barrier counts the 16 epilogue
+// warps of the pair (the peer's arrive over the cluster address).  'empty' and accumulator-full barriers are local and
+// receive the leader's multicast commits, so the two rings run in lockstep.
+//
 // S2D (conv3x3 on a tensor stored space-to-depth): a [n, 2h, 2w, 16] activation kept as [n, h, w, 4 x 16] (channel
 // group = pixel parity (ph,pw), the layout the sub-pixel conv's GEMM produces before any pixel shuffle) is one
 // 64-channel chunk whose K=16 slice k IS parity plane k.  A 3x3 conv at the full resolution is then a 3x3 conv over
 // blocks with 4x16 outputs in which plane (ph,pw) only meets taps {1-ph,2-ph} x {1-pw,2-pw}: the MMA loop issues those
 // 16 of the 36 (tap, k) pairs (N = 64 or 16 instead of 16 per MMA, 2.25x fewer MMAs per output pixel) and rows of
 // 128 bytes go in and out by TMA.  The head variant writes the 4 logits / mask bytes of a block to its 2x2 pixels.
-template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, int SPX = 0, bool S2D = false>
+template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, int SPX = 0, bool S2D = false, bool CG2 = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -260,7 +272,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     tma_prefetch_desc(&tm_wgt);
     if (SPX == 1) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
   } else if (threadIdx.x == 64) {
-    for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), 8); }
+    for (int a = 0; a < 4; ++a) { mbar_init(accf_bar(a), 1); mbar_init(acce_bar(a), CG2 ? 16 : 8); }
     for (int w = 0; w < 8; ++w) mbar_init(resbar(w), 1);
     fence_mbar_init();
     if (p.ep_tma) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
@@ -270,15 +282,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     if (A_TMA) { tma_prefetch_desc(&tm_a0); tma_prefetch_desc(&tm_a1); }
     else if (p.mix) tma_prefetch_desc(&tm_a1);
   }
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;      // CTA pair: rank 0 leads (issues the MMAs, owns the full barriers)
+  // the peer's barriers must exist before anything signals them: cluster barrier, its wait overlapped with the TMEM alloc
+  if (CG2) cluster_arrive();
   if (warp == 1) {
-    tmem_alloc(smem_u32(s_tmem_slot), p.tmem_cols);
-    tmem_relinquish();
+    if (CG2) { tmem_alloc_cg2(smem_u32(s_tmem_slot), p.tmem_cols); tmem_relinquish_cg2(); }
+    else { tmem_alloc(smem_u32(s_tmem_slot), p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CG2) cluster_wait();
   const uint32_t tmem_base = *s_tmem_slot;
   const int G = gridDim.x;
+  // tile sequence of this CTA: tiles blockIdx.x, +G, ... ; a CTA pair walks pair-tiles (two M tiles of one N tile)
+  const int t_first = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_end = CG2 ? (p.total_tiles >> 1) : p.total_tiles;
+  const int t_step = CG2 ? (G >> 1) : G;
+  auto tile_of = [&](int tl) {
+    if (!CG2) return tl;
+    const int mu = fast_div(tl, p.div_ntiles);
+    return (2 * mu + (int)crank) * p.n_tiles + (tl - mu * p.n_tiles);
+  };
+  // the leader's copy of a barrier, as a cluster address (the leader's own barrier for the leader)
+  auto lead = [&](uint32_t bar) { return CG2 ? mapa_u32(bar, 0) : bar; };
   // accumulator sets in TMEM (2 or 4): the MMA -> epilogue -> MMA hand-back is a ~3000-cycle round trip even
   // with nothing to do, so short tiles need more than two sets in flight
   const int nacc_log2 = p.nacc_log2, nacc_mask = (1 << nacc_log2) - 1;
@@ -299,7 +326,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     } else {
       const bool leader = elect_one();
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
+      for (int tl = t_first; tl < t_end; tl += t_step) {
+        const int tile = tile_of(tl);
         const int ncol = (tile - fast_div(tile, p.div_ntiles) * p.n_tiles) * p.block_n;
         if (SPX) {
           // slices in the MMA warp's issue order; each carries only the rows (GEMM columns) its tap can reach
@@ -335,11 +363,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
             if (leader) {
               mbar_wait(bempty_bar(s), ph ^ 1u);
-              mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)p.kpb * slice_tx);
               const uint32_t dst = b_base + (uint32_t)s * b_stage_bytes;
-              for (int j = 0; j < p.kpb; ++j)
-                tma_load_2d(dst + (uint32_t)j * p.b_slice_bytes, &tm_wgt, bfull_bar(s),
-                            (tap0 + j) * p.cin_total + ch * KC, ncol);
+              if (CG2) {
+                // this CTA's half of the rows of every slice; the bytes of BOTH CTAs complete on the leader's barrier,
+                // which only the leader arms (a remote arrive per slice costs the peer's producer ~500 cycles)
+                const uint32_t fb = lead(bfull_bar(s));
+                if (crank == 0) mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)p.kpb * slice_tx);
+                for (int j = 0; j < p.kpb; ++j)
+                  tma_load_2d_cg2(dst + (uint32_t)j * p.b_slice_bytes, &tm_wgt, fb, (tap0 + j) * p.cin_total + ch * KC,
+                                  ncol + (int)crank * (p.block_n >> 1));
+              } else {
+                mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)p.kpb * slice_tx);
+                for (int j = 0; j < p.kpb; ++j)
+                  tma_load_2d(dst + (uint32_t)j * p.b_slice_bytes, &tm_wgt, bfull_bar(s),
+                              (tap0 + j) * p.cin_total + ch * KC, ncol);
+              }
             }
             if (++s == p.b_stages) { s = 0; ph ^= 1u; }
           }
@@ -348,7 +386,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one elected thread)
-    const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+    const uint32_t idesc = make_idesc_bf16(CG2 ? 2 * kTileM : kTileM, p.block_n);
+    auto commit = [&](uint32_t bar) { if (CG2) umma_commit_cg2(bar, (uint16_t)3); else umma_commit(bar); };
     // A descriptors, per stage layout.  swizzled pixel-major (TMA box): hi = SBO (one halo row) | version | swizzle,
     // LBO unused.  no-swizzle planes (cp.async gather): hi = SBO (halo_w x 16 B) | version, LBO = plane stride.
     constexpr uint32_t a_hi_sw = (((uint32_t)PW * ROWB) >> 4) | (1u << 14) | (B_LAYOUT << 29);
@@ -365,12 +404,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const bool skip_mma = p.dbg & 2;
     const uint32_t idesc_half = make_idesc_bf16(kTileM, SPX == 1 ? p.block_n >> 1 : p.block_n);
     const uint32_t idesc_quarter = make_idesc_bf16(kTileM, SPX == 1 ? p.block_n >> 2 : p.block_n);
-    if (elect_one()) {
+    if (elect_one() && (!CG2 || crank == 0)) {
       if (RESIDENT) mbar_wait(bres_bar, 0);
       int sa = 0; uint32_t pha = 0;
       int sb = 0; uint32_t phb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
+      for (int tl = t_first; tl < t_end; tl += t_step, ++it) {
+      const int tile = tile_of(tl);
         const int acc = it & nacc_mask;
         const uint32_t tmem_acc = tmem_base + (uint32_t)acc * (TG * bn);
         mbar_wait_fast(acce_bar(acc), ((uint32_t)(it >> nacc_log2) & 1u) ^ 1u);
@@ -409,17 +449,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                     if (!((r == 1 - ph || r == 2 - ph) && (c == 1 - pw || c == 2 - pw))) continue;
                   }
                   if (tap == 0 && k == (S2D ? 3 : 0))
-                    umma_halo<false>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
-                                     b_lo + 2u * k, b_hi, idesc, (uint32_t)ch);
+                    umma_halo<false, CG2>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
+                                          b_lo + 2u * k, b_hi, idesc, (uint32_t)ch);
                   else
-                    umma_halo<true>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
-                                    b_lo + 2u * k, b_hi, idesc, 1u);
+                    umma_halo<true, CG2>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
+                                         b_lo + 2u * k, b_hi, idesc, 1u);
                 }
               }
               b_lo += b_slice_units;
               if (!RESIDENT && ++j == p.kpb) {
                 j = 0;
-                umma_commit(bempty_bar(sb));
+                commit(bempty_bar(sb));
                 if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
               }
             }
@@ -453,7 +493,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                     else umma_halo<true>(d, a_st + (shift + 8u * g) * (ROWB >> 4) + 2u * k, a_hi_sw, b_st + 2u * k, b_hi, idesc_t, 1u);
                   }
                 }
-                umma_commit(bempty_bar(sb));
+                commit(bempty_bar(sb));
                 if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
               };
               if (SPX == 2) {
@@ -485,14 +525,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             const int nt_ch = (SPX == 2) ? ((par2 >> 1) + 1) * ((par2 & 1) + 1) : ((SPX && ch >= p.split_chunk) ? 4 : NT);
             for (int tap0 = 0; tap0 < nt_ch; tap0 += p.kpb) {
               mbar_wait_fast(bfull_bar(sb), phb);
-              umma_commit(bempty_bar(sb));
+              commit(bempty_bar(sb));
               if (++sb == p.b_stages) { sb = 0; phb ^= 1u; }
             }
           }
-          umma_commit(aempty_bar(sa));
+          commit(aempty_bar(sa));
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
-        umma_commit(accf_bar(acc));
+        commit(accf_bar(acc));
         halo_trace(p, 162 + 3 * it);
       }
     }
@@ -523,7 +563,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     uint32_t res_cnt = 0;                      // residual boxes consumed by this warp (barrier parity)
     pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++it) {
+    for (int tl = t_first; tl < t_end; tl += t_step, ++it) {
+      const int tile = tile_of(tl);
       const int acc = it & nacc_mask;
       const HaloTile t = halo_decode<TG>(p, tile);
       const int oh = t.h0 + hi;
@@ -719,7 +760,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       // every tcgen05.ld of this accumulator set has completed (tcgen05.wait::ld above): hand the set back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acce_bar(acc));
+      if (lane == 0) { if (CG2 && crank != 0) mbar_arrive_cluster(lead(acce_bar(acc))); else mbar_arrive(acce_bar(acc)); }
       if (warp == 2 && lane == 0) halo_trace(p, 401 + 2 * it);
     }
     if (tma_out && lane == 0) bulk_wait_read<0>();     // smem must outlive the last store's read
@@ -734,13 +775,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     if (A_TMA) {
       // one thread, one TMA box per stage; out-of-image coordinates are zero-filled (= conv padding)
       if (lt == 0) {
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
+        for (int tl = t_first; tl < t_end; tl += t_step) {
+        const int tile = tile_of(tl);
           const HaloTile t = halo_decode<TG>(p, tile);
           const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
           for (int ch = 0; ch < p.chunks; ++ch) {
             mbar_wait(aempty_bar(s), ph ^ 1u);
             halo_trace(p, 16 + 2 * nstage);
-            if (!(p.dbg & 1)) {
+            if (CG2) {       // both CTAs' boxes complete on the leader's barrier (CG2 kernels have one source)
+              const uint32_t fa = lead(afull_bar(s));
+              if (!(p.dbg & 1)) {
+                if (crank == 0) mbar_arrive_expect_tx(afull_bar(s), 2u * (uint32_t)NPIX * ROWB);   // both CTAs' boxes
+                tma_load_4d_cg2(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, fa, ch * KC, wbase * p.a_scale,
+                                hbase * p.a_scale, t.img);
+              } else if (crank == 0) {
+                mbar_arrive(afull_bar(s));
+              }
+            } else if (!(p.dbg & 1)) {
               mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
               if (ch < p.split_chunk)
                 tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase * p.a_scale,
@@ -763,7 +814,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         }
       }
     } else
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
+    for (int tl = t_first; tl < t_end; tl += t_step) {
+        const int tile = tile_of(tl);
       const HaloTile t = halo_decode<TG>(p, tile);
       const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
       for (int ch = 0; ch < p.chunks; ++ch) {
@@ -813,7 +865,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (CG2) cluster_sync_all();       // the peer may still signal this CTA's barriers / the leader still reads its smem
+  if (warp == 1) { if (CG2) tmem_dealloc_cg2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols); }
   if (threadIdx.x == 0) halo_trace_cta(p, 1);
 }
 

@@ -101,6 +101,9 @@ static bool pdl_enabled() {
 // caller may have produced the weights or the bias on this stream one kernel earlier.
 static thread_local int g_plan_depth = 0;
 struct PlanScope { PlanScope() { ++g_plan_depth; } ~PlanScope() { --g_plan_depth; } };
+// same, as 2-CTA clusters (CTA pairs of the cta_group::2 kernels)
+template <typename... KArgs, typename... Args>
+static void launch_pdl_pairs(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args);
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -110,6 +113,20 @@ static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool op_pdl = []{ const char* e = getenv("UWM_OP_PDL"); return e && e[0] == '1'; }();   // bench tools: time single ops as the plan runs them
   cfg.attrs = attr; cfg.numAttrs = (pdl_enabled() && (g_plan_depth > 0 || op_pdl)) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl_pairs(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool op_pdl = []{ const char* e = getenv("UWM_OP_PDL"); return e && e[0] == '1'; }();
+  cfg.attrs = attr; cfg.numAttrs = (pdl_enabled() && (g_plan_depth > 0 || op_pdl)) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -158,7 +175,7 @@ struct ConvSpec {
 
 struct ConvLaunch {
   int halo = 0;                   // 0: conv_tc_kernel (args), 1: conv_halo_kernel (hargs)
-  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0, spx = 0, s2d = 0;   // halo: template instantiation
+  int kh = 0, kw = 0, kc = 0, tg = 0, resident = 0, a_tma = 0, spx = 0, s2d = 0, cg2 = 0;   // halo: template instantiation
   CUtensorMap tm_act, tm_wgt, tm_out, tm_res, tm_a0, tm_a1;
   ConvKArgs args;
   HaloKArgs hargs;
@@ -556,8 +573,22 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.div_ntiles = make_fastdiv(a.n_tiles);
   a.div_tw = make_fastdiv(a.tiles_w);
   a.div_th = make_fastdiv(a.tiles_h);
-  const unsigned grid = (unsigned)std::min(a.total_tiles, sms);
-  a.b_slice_bytes = ((uint32_t)bn * kc * 2u + 1023u) & ~1023u;
+  // CTA pairs (cta_group::2) for the streamed 3x3 kernels fed by TMA from one source: two M tiles of one N tile share
+  // every weight slice, each CTA loading half of its rows
+  // Measured (r34 512x512 B=16): it pays where a tile's streamed bytes outrun the fabric's ~43 B/clk per SM - layer4
+  // (1.18 MB of weights per 18.4 k tensor cycles: 20.3 -> 18.3 us) - and costs ~7 % on layer2/3 (32 B/clk; the pair's
+  // TMEM allocation and commit round trips add ~2.5 k cycles per launch and the MMA rate does not improve).
+  // UWM_CG2=0: never, 2: wherever eligible.
+  static const int cg2_mode = []{ const char* e = getenv("UWM_CG2"); return e ? atoi(e) : 1; }();
+  const double cg2_bytes_per_clk = ((double)halo_npix(tg, kh, kw) * cin_total * 2 + (double)bn * nk * kc * 2) /
+                                   ((double)tg * nk * (kc / 16) * (bn >= 256 ? 128.0 : 32.0 + bn / 4.0));
+  const bool cg2 = cg2_mode > 0 && (cg2_mode == 2 || cg2_bytes_per_clk > 50.0) && !best.resident && a_tma && !s.x2 &&
+                   !s.s2d && !s.head && !s.shuffle && !s.in_stride2 && kc == 64 && kh == 3 && kw == 3 &&
+                   (m_tiles % 2 == 0) && bn % 32 == 0 && a.total_tiles >= 2;
+  L->cg2 = cg2 ? 1 : 0;
+  unsigned grid = (unsigned)std::min(a.total_tiles, sms);
+  if (cg2) grid &= ~1u;
+  a.b_slice_bytes = (((uint32_t)bn >> (cg2 ? 1 : 0)) * kc * 2u + 1023u) & ~1023u;    // a pair holds half of the rows per CTA
   const size_t resident_bytes = (size_t)nk * a.b_slice_bytes;
   if (best.resident) {
     a.kpb = 1; a.b_stages = 1;
@@ -605,7 +636,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     if (e && e[0] == '1')
       fprintf(stderr, "halo conv %dx%dx%d cin=%d(+%d%s) cout=%d %dx%d: bn=%d tg=%d kc=%d chunks=%d tiles=%d grid=%u a_stages=%d (%zu B) %s kpb=%d b_stages=%d\n",
               s.n, s.h, s.w, s.cin, s.cin2, s.up1 ? ",up" : "", s.cout, kh, kw, bn, tg, kc, a.chunks, a.total_tiles, grid,
-              a.a_stages, a_stage_bytes, best.resident ? "B resident" : "B streamed", a.kpb, a.b_stages); }
+              a.a_stages, a_stage_bytes, best.resident ? "B resident" : (cg2 ? "B streamed, CTA pairs" : "B streamed"), a.kpb, a.b_stages); }
   L->grid = grid;
   const size_t b_total = best.resident ? resident_bytes : (size_t)a.b_stages * a.kpb * a.b_slice_bytes;
   L->smem = 1024 + b_total + (size_t)a.a_stages * a_stage_bytes + stg_bytes + 1024 + (size_t)s.cout_pad * 4;
@@ -616,7 +647,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   const cuuint64_t ktot = (cuuint64_t)s.ntaps * cin_total;
   cuuint64_t dims[2] = {ktot, (cuuint64_t)s.cout_pad};
   cuuint64_t strides[1] = {ktot * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(cg2 ? bn / 2 : bn)};
   cuuint32_t est[2] = {1, 1};
   CUresult r = enc(&L->tm_wgt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims, strides, box,
                    est, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -814,7 +845,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   if (!L) {                                                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<KC, KH, KW, TG, RES, AT>,                                    \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                    \
-  } else if (!L->spx && !L->s2d && L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES && \
+  } else if (!L->spx && !L->s2d && !L->cg2 && L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES && \
              (L->a_tma != 0) == AT) {                                                                           \
     launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
                L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                                                   \
@@ -833,6 +864,19 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   UWM_HALO_CASE1(64, 1, 1, 1, false, true) UWM_HALO_CASE1(64, 1, 1, 2, false, true)
 #undef UWM_HALO_CASE
 #undef UWM_HALO_CASE1
+  // CTA pairs (CG2): streamed 3x3, 64-channel chunks, TMA-fed, launched as 2-CTA clusters
+#define UWM_HALO_CG2(TG)                                                                                          \
+  if (!L) {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, false, true, 0, false, true>,                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
+  } else if (L->cg2 && L->tg == TG) {                                                                             \
+    launch_pdl_pairs(conv_halo_kernel<64, 3, 3, TG, false, true, 0, false, true>, L->grid, kHaloThreads, L->smem, \
+                     st, L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                          \
+    return UWM_OK;                                                                                                \
+  }
+  UWM_HALO_CG2(1) UWM_HALO_CG2(2)
+#undef UWM_HALO_CG2
+  if (L && L->cg2) return fail(UWM_ESTATE, "halo conv: no CTA-pair kernel for tg=%d", L->tg);
   // space-to-depth 3x3 convs (S2D): one 64-channel chunk = 4 parity planes x 16, resident weights, TMA-fed
 #define UWM_HALO_S2D(TG)                                                                                          \
   if (!L) {                                                                                                       \
