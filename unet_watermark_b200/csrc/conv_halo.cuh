@@ -1,6 +1,8 @@
-// Halo-resident implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) for stride-1 k x k convs
-// (3x3, the stem's 4x4 over the space-to-depth input, 1x1), with the decoder's nearest-2x upsample and
-// skip concat fused into the activation loader, and a sub-pixel mode for the skip-less decoder conv.
+// Halo-resident implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): every conv of the Unet plan.
+// Stride-1 k x k convs (3x3, the stem's 4x4 over the space-to-depth input, 1x1) with the decoder's nearest-2x
+// upsample and skip concat fused into the activation loader, plus the forms documented at the kernel template
+// below: sub-pixel convs over an upsampled (and concatenated) input (SPX = 1), stride-2 convs over the input's
+// parity planes (SPX = 2), convs on space-to-depth tensors (S2D) and CTA pairs sharing the weights (CG2).
 //
 //   out[n,h,w,co] = epilogue( sum_{tap,ci} in[n, h+dh(tap), w+dw(tap), ci] * wgt[co, tap, ci] )
 //   in = concat_c( up2x?(src0), src1 )          (src1 optional; up2x = F.interpolate(nearest, x2))
