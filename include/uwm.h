@@ -66,6 +66,10 @@ extern "C" {
                                  chunk, per halo tap (r,c) with r in {1} (ph = 0) or {0,1} (ph = 1), c likewise:
                                  w[co, ci, kr, kc], kr = 1 if ph == 0 else (0 if r == 0 else 2), kc likewise
                                  (packing.pack_s2_planes); the same 9*cin values as UWM_PACK_TAPS, reordered      */
+#define UWM_PACK_TAPS_SKIP_PART 6       /* UWM_PACK_TAPS of the LAST cin_skip input channels of the conv (the skip half of a
+                                          decoder conv1 run as two launches); bias = the conv's folded bias            */
+#define UWM_PACK_UP2X_SHUFFLE_X_PART 7 /* UWM_PACK_UP2X_SHUFFLE of the FIRST cin - cin_skip input channels (the upsampled
+                                          half); bias = zeros (the skip-half launch carried it)                         */
 #define UWM_PACK_STEM_S2D 1   /* 7x7/s2 stem as 4x4/s1 over the 2x2 space-to-depth input:
                                  [64][4*4][16] bf16, channel = (ph*2+pw)*3 + c, 12..15 zero      */
 
@@ -117,6 +121,14 @@ int uwm_conv2d_upcat_nhwc_bf16(const void* d_x, int n, int h, int w, int c_x, in
 int uwm_conv2d_up2x_shuffle_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
                                       const void* d_wgt /*[4*cout][9*cin]*/, const float* d_bias /*[4*cout]*/,
                                       int cout, int relu, void* d_y, int y_pitch, void* stream);
+
+/* Sub-pixel conv with a residual added at the shuffled output position before the ReLU; cout up to 64 as above, or 128 /
+ * 256 (cin a multiple of 64): then every output parity is its own N tile and streams 4 of the 9 taps.  d_res (may be
+ * NULL) is [n,2h,2w,cout].  With uwm_conv2d_nhwc_bf16 on the skip source this is DecoderBlock conv1 in two launches. */
+int uwm_conv2d_up2x_shuffle_res_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                          const void* d_wgt, const float* d_bias, int cout,
+                                          const void* d_res, int res_pitch, int relu, void* d_y, int y_pitch,
+                                          void* stream);
 
 /* The same sub-pixel form for the decoder conv1 WITH a skip: y = act(conv3x3(concat(nearest-2x(x), skip)) + bias).
  * x[n,h,w,c_x]; skip[n,2h,2w,c_skip]; y[n,2h,2w,cout]; c_x and c_skip multiples of 64, cout a multiple of 16, <= 64.
@@ -188,7 +200,8 @@ typedef struct uwm_layer_desc {
   int64_t w_elems;        /* bf16 elements expected by uwm_model_set_layer                   */
   int64_t b_elems;        /* fp32 elements expected                                           */
   double  flops_per_image;/* 2*MACs of the reference conv (algorithmic, un-padded)            */
-  int32_t cin_skip;       /* UWM_PACK_UPCAT_SUBPIXEL: channels of the skip source (last cin_skip of cin) */
+  int32_t cin_skip;       /* channels of the skip source of the reference conv (its last cin_skip input channels):
+                             UWM_PACK_UPCAT_SUBPIXEL, and the two _PART packings, whose `cin` is the part's own */
   int32_t reserved;
 } uwm_layer_desc;
 

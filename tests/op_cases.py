@@ -99,3 +99,12 @@ S2P_CASES = [
     ("s2planes_persistent",  2, 256, 256, 64, 128, True),     # several tiles per CTA
     ("r50_l4_conv2_s2planes", 1, 16, 16, 512, 512, True),     # long K (72 slices), four N tiles
 ]
+
+# Sub-pixel conv with one N tile per output parity (Cout 128 / 256) and the residual added in the pixel-shuffle epilogue -
+# uwm_conv2d_up2x_shuffle_res_nhwc_bf16.   (name, n, h_lo, w_lo, cin, cout, relu, with_residual)
+SHUFFLE_RES_CASES = [
+    ("d1_x_part_256_128",       1, 16, 16, 256, 128, True, True),     # decoder block 1's upsampled half
+    ("d0_x_part_512_256",       2, 8, 8, 512, 256, True, True),       # decoder block 0's upsampled half (N tile = 256)
+    ("subpixel_par_ragged",     1, 12, 20, 64, 128, False, False),    # partial tiles, no residual
+    ("subpixel_par_persistent", 2, 64, 64, 128, 128, True, True),     # several tiles per CTA
+]

@@ -7,7 +7,8 @@ import torch.nn.functional as F
 
 import zlib
 
-from tests.op_cases import CONV_CASES, S2D_CASES, S2P_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES
+from tests.op_cases import (CONV_CASES, S2D_CASES, S2P_CASES, SHUFFLE_CASES, SHUFFLE_RES_CASES, SPX_CASES,
+                            UPCAT_CASES)
 from unet_watermark_b200 import _lib, ops, packing
 
 
@@ -205,6 +206,33 @@ def test_s2d_head_matches_fp32_reference(case, cuda_device):
     _, mask2 = ops.head_s2d(_s2d_nhwc(x), packing.pack_s2d_conv3x3(wt, 16), packing.pad_bias(bias, 16), threshold=0.5,
                             want_logits=False)
     assert torch.equal(mask, mask2)
+
+
+@pytest.mark.parametrize("case", SHUFFLE_RES_CASES, ids=[c[0] for c in SHUFFLE_RES_CASES])
+def test_subpixel_parity_tiles_with_residual(case, cuda_device):
+    """act(conv3x3(interpolate(x, 2, nearest)) + bias + residual) with Cout 128 / 256: every output parity is its own N
+    tile and issues 4 of the 9 taps.  Same tolerance as the other sub-pixel conv (pre-summed weights rounded once)."""
+    name, n, h, w, cin, cout, relu, with_res = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(_seed(name))
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(n, 2 * h, 2 * w, cout, generator=g).to(dev).to(torch.bfloat16) if with_res else None
+    before = _lib.load().uwm_kernel_launch_count()
+    out = ops.conv2d_up2x_shuffle_res(x, packing.pack_up2x_shuffle(wt), bias.repeat(4).contiguous(), residual=res, relu=relu)
+    assert _lib.load().uwm_kernel_launch_count() == before + 1
+    xi = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    conv = F.conv2d(xi, wt.to(torch.bfloat16).float(), bias, padding=1)
+    ref = conv + res.float().permute(0, 3, 1, 2) if res is not None else conv
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    # the conv term carries the extra weight rounding; where it cancels against the residual the bound must follow the
+    # conv's magnitude, not the (small) sum's
+    scale = torch.maximum(ref.abs(), conv.abs().permute(0, 2, 3, 1)).clamp_min(1.0)
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1.5e-2 * scale).all()), f"max err {err.max().item()}"
 
 
 def test_conv_rejects_bad_arguments(cuda_device):

@@ -208,3 +208,32 @@ def test_s2_planes_packing_equals_stride2_conv():
     assert torch.allclose(acc, ref, atol=1e-4, rtol=1e-4)
     # a permutation of pack_taps' columns: same multiset of values per output channel
     assert torch.equal(wp.sort(dim=1).values, packing.pack_taps(wt).float().sort(dim=1).values)
+
+
+def test_two_launch_upcat_split_equals_the_single_conv():
+    """Decoder blocks 0/1: conv3x3(cat(up2x(x), skip)) == conv3x3(skip; last c_skip channels, bias) + sub-pixel conv of
+    the first c_x channels (no bias) - the two launches the plan issues (UWM_PACK_TAPS_SKIP_PART /
+    UWM_PACK_UP2X_SHUFFLE_X_PART), each N tile of the second using only the 2x2 taps of its parity."""
+    g = torch.Generator().manual_seed(8)
+    cout, c_x, c_s, h, w = 8, 6, 5, 4, 5
+    wt = torch.randn(cout, c_x + c_s, 3, 3, generator=g)
+    b = torch.randn(cout, generator=g)
+    x = torch.randn(2, c_x, h, w, generator=g)
+    skip = torch.randn(2, c_s, 2 * h, 2 * w, generator=g)
+    ref = F.conv2d(torch.cat([F.interpolate(x, scale_factor=2, mode="nearest"), skip], 1), wt, b, padding=1)
+    part = F.conv2d(skip, wt[:, c_x:], b, padding=1)                                   # launch 1 (bias here)
+    wq = packing.pack_up2x_shuffle_f32(wt[:, :c_x]).reshape(2, 2, cout, 3, 3, c_x)     # [qh, qw, co, a, b, ci]
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for qh in range(2):
+        for qw in range(2):
+            acc = torch.zeros(2, cout, h, w)
+            for a in (qh, qh + 1):                      # the N tile of parity (qh,qw) issues taps {qh,qh+1} x {qw,qw+1}
+                for bb in (qw, qw + 1):
+                    acc += torch.einsum("ok,nkhw->nohw", wq[qh, qw, :, a, bb, :], xp[:, :, a:a + h, bb:bb + w])
+            # ... and every other tap of that parity's weights is structurally zero
+            rest = wq[qh, qw].clone()
+            rest[:, qh:qh + 2, qw:qw + 2, :] = 0
+            assert not rest.any()
+            out[:, :, qh::2, qw::2] = acc
+    assert torch.allclose(out + part, ref, atol=1e-4, rtol=1e-4)

@@ -27,6 +27,8 @@ SHAPES = [  # name, n, h, w, cin (x), cskip, cout, upsample
     ("dec3 up64+64->32 @256", 16, 128, 128, 64, 64, 32, True),
     ("dec3 spx up64+64->32 @256", 16, 128, 128, 64, 64, 32, "spx"),
     ("dec2 spx up128+64->64 @128", 16, 64, 64, 128, 64, 64, "spx"),
+    ("dec0 xpart up512->256 @32", 16, 16, 16, 512, 0, 256, "par"),    # sub-pixel, one N tile per parity, + residual
+    ("dec1 xpart up256->128 @64", 16, 32, 32, 256, 0, 128, "par"),
     ("dec3 32->32 @256", 16, 256, 256, 32, 0, 32, False),
     ("dec4 up32->16 @512", 16, 256, 256, 32, 0, 16, True),
     ("dec4 16->16 @512", 16, 512, 512, 16, 0, 16, False),
@@ -51,7 +53,13 @@ def main():
         ho, wo = (2 * h, 2 * w) if up else (h, w)
         skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
         cin = cx + cs
-        if up in ("s2d", "s2dhead"):
+        if up == "par":
+            wt = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+            wp = packing.pack_up2x_shuffle(wt)
+            b = torch.zeros(4 * cout, device=dev)
+            out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+            par_res = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16)
+        elif up in ("s2d", "s2dhead"):
             ho, wo, cin = h, w, 16
             wt = torch.randn(cout, 16, 3, 3, device=dev) / 12
             wp = packing.pack_s2d_conv3x3(wt, 16 if cout == 1 else 0)
@@ -65,7 +73,9 @@ def main():
         times = []
 
         def run():
-            if up == "s2d":
+            if up == "par":
+                ops.conv2d_up2x_shuffle_res(x, wp, b, residual=par_res, relu=True, out=out)
+            elif up == "s2d":
                 ops.conv2d_s2d(x, wp, b, relu=True, out=out)
             elif up == "s2dhead":
                 ops.head_s2d(x, wp, b, threshold=0.5, want_logits=False)

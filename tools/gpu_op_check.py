@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.op_cases import CONV_CASES, S2D_CASES, S2P_CASES, SHUFFLE_CASES, SPX_CASES, UPCAT_CASES  # noqa: E402
+from tests.op_cases import CONV_CASES, S2D_CASES, S2P_CASES, SHUFFLE_CASES, SHUFFLE_RES_CASES, SPX_CASES, UPCAT_CASES  # noqa: E402
 from unet_watermark_b200 import ops, packing  # noqa: E402
 
 
@@ -140,6 +140,35 @@ def main():
         except Exception as ex:  # noqa: BLE001
             nfail += 1
             print(f"EXC  subpx {case[0]}: {ex}", flush=True)
+            traceback.print_exc()
+            if "CUDA" in str(ex) or "fault" in str(ex):
+                print("aborting after CUDA error")
+                sys.exit(2)
+
+    for case in SHUFFLE_RES_CASES:
+        if args.filter not in case[0]:
+            continue
+        try:
+            name, n, h, w, cin, cout, relu, with_res = case
+            g = torch.Generator(device="cpu").manual_seed(0)
+            x = torch.randn(n, h, w, cin, generator=g).to(dev).to(torch.bfloat16)
+            wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev)
+            bias = torch.randn(cout, generator=g).to(dev)
+            res = torch.randn(n, 2 * h, 2 * w, cout, generator=g).to(dev).to(torch.bfloat16) if with_res else None
+            out = ops.conv2d_up2x_shuffle_res(x, packing.pack_up2x_shuffle(wt), bias.repeat(4).contiguous(), residual=res, relu=relu)
+            torch.cuda.synchronize()
+            xi = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+            conv = F.conv2d(xi, wt.to(torch.bfloat16).float(), bias, padding=1)
+            ref = conv + res.float().permute(0, 3, 1, 2) if res is not None else conv
+            ref = (ref.relu() if relu else ref).permute(0, 2, 3, 1)
+            err = (out.float() - ref).abs()
+            scale = torch.maximum(ref.abs(), conv.abs().permute(0, 2, 3, 1)).clamp_min(1.0)
+            bad = (err > 1.5e-2 * scale).float().mean().item()
+            print(f"{'OK  ' if bad == 0 else 'FAIL'} subpar {name:<24s} max_err={err.max().item():.4g} ref_max={ref.abs().max().item():.4g} bad_frac={bad:.4g}", flush=True)
+            nfail += (bad != 0)
+        except Exception as ex:  # noqa: BLE001
+            nfail += 1
+            print(f"EXC  subpar {case[0]}: {ex}", flush=True)
             traceback.print_exc()
             if "CUDA" in str(ex) or "fault" in str(ex):
                 print("aborting after CUDA error")

@@ -22,6 +22,8 @@ PACK_UP2X_SHUFFLE = 2
 PACK_UPCAT_SUBPIXEL = 3
 PACK_S2D_CONV = 4
 PACK_S2_PLANES = 5
+PACK_TAPS_SKIP_PART = 6
+PACK_UP2X_SHUFFLE_X_PART = 7
 
 
 class LayerDesc(C.Structure):
@@ -52,6 +54,8 @@ SIGNATURES = {
                                              C.c_int, _P]),
     "uwm_conv2d_up2x_shuffle_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                                     C.c_int, _P, C.c_int, _P]),
+    "uwm_conv2d_up2x_shuffle_res_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
+                                                        _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "uwm_conv2d_upcat_subpixel_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int,
                                                       C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "uwm_conv2d_s2_planes_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,

@@ -195,6 +195,12 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 // with a 2x2 block halo at origin -1 plane ph meets halo rows {1} (ph = 0) or {0,1} (ph = 1): 9 (plane, tap) pairs,
 // one per kernel tap, each a full-N MMA group over a dense TMA-written stage - the stride never reaches the MMA.
 //
+// SPX == 3 (sub-pixel conv over an upsampled input with 4*Cout > 256 GEMM columns): one N tile per output parity
+// (block_n = Cout); parity (qh,qw) only meets the 2x2 taps {qh,qh+1} x {qw,qw+1} of the 3x3 source neighbourhood, so
+// an N tile streams and issues 4 of the 9 taps.  The pixel-shuffle epilogue can add a residual (the partial sum of
+// the skip half of a decoder conv1, computed by an ordinary conv launch) before the ReLU; with Cout >= 64 it is the
+// ordinary TMA-store epilogue over an element-stride-2 view of the output (one view serves the four parities).
+//
 // CG2 (CTA pair, streamed weights): the two CTAs of a 2-CTA cluster work on two M tiles of the same N tile and share
 // every weight slice - each loads HALF of its rows (block_n/2) and the leader issues one M = 256 tcgen05.mma.cta_group::2
 // per tap / K step that reads A from both CTAs' stages (same offsets: the rings run in lockstep), B half from each, and
@@ -217,6 +223,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                  const __grid_constant__ HaloKArgs p) {
   constexpr int NT = KH * KW;
+  constexpr bool SPXP = (SPX == 1 || SPX == 2);            // chunk / slice sequencing of the parity-plane forms
   constexpr int CPS = KC / 8;                               // 8-channel planes per stage
   constexpr int LOG2_CPS = (KC == 64) ? 3 : (KC == 32) ? 2 : 1;
   constexpr int PW = halo_pw(TG, KW);
@@ -331,7 +338,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       for (int tl = t_first; tl < t_end; tl += t_step) {
         const int tile = tile_of(tl);
         const int ncol = (tile - fast_div(tile, p.div_ntiles) * p.n_tiles) * p.block_n;
-        if (SPX) {
+        if (SPXP) {
           // slices in the MMA warp's issue order; each carries only the rows (GEMM columns) its tap can reach
           // (see spx_tap): all bn, half of them or a quarter, through the map with the matching box height
           int sl = 0, par = 0, cc = 0;       // no divisions here: this one thread feeds ~25 slices per tile
@@ -358,6 +365,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               if (++s == p.b_stages) { s = 0; ph ^= 1u; }
             }
             if (!is_x && ++cc == p.spx_cpp) { cc = 0; ++par; }
+          }
+          continue;
+        }
+        if (SPX == 3) {      // the 2x2 taps of this N tile's output parity, one slice per stage
+          const int q = ncol / p.block_n, qh = q >> 1, qw = q & 1;
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            for (int t = 0; t < 4; ++t) {
+              if (leader) {
+                const int tap = (qh + (t >> 1)) * KW + qw + (t & 1);
+                mbar_wait(bempty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(bfull_bar(s), slice_tx);
+                tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tm_wgt, bfull_bar(s), tap * p.cin_total + ch * KC, ncol);
+              }
+              if (++s == p.b_stages) { s = 0; ph ^= 1u; }
+            }
           }
           continue;
         }
@@ -470,7 +492,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           using I2 = std::integral_constant<int, 2>;
           using IH = std::integral_constant<int, KH>; using IW = std::integral_constant<int, KW>;
           if (!skip_mma) {
-            if (SPX) {
+            if (SPXP) {
               // One tap (R,C) of the 3x3 block neighbourhood.  Row R = 0 only reaches output parity qh = 0, R = 2 only
               // qh = 1, R = 1 both (same for columns), so with GEMM columns ordered (qh, qw, co) the tap needs
               // N = bn (R == 1), bn/2 at column qh*bn/2 (R != 1, C == 1) or bn/4 at column (2qh+qw)*bn/4: fewer
@@ -519,12 +541,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                 else { spx_tap(I0{}, I0{}, 1u); spx_tap(I0{}, I1{}, 1u); spx_tap(I1{}, I0{}, 1u); spx_tap(I1{}, I1{}, 1u); }
               }
             }
+            else if (SPX == 3) {
+              const int q = tile - fast_div(tile, p.div_ntiles) * p.n_tiles;      // N tile = output parity (qh,qw)
+              if (q == 0) issue_chunk(std::true_type{}, I0{}, I0{}, I2{}, I2{});
+              else if (q == 1) issue_chunk(std::true_type{}, I0{}, I1{}, I2{}, I2{});
+              else if (q == 2) issue_chunk(std::true_type{}, I1{}, I0{}, I2{}, I2{});
+              else issue_chunk(std::true_type{}, I1{}, I1{}, I2{}, I2{});
+            }
             else if (A_TMA) issue_chunk(std::true_type{}, I0{}, I0{}, IH{}, IW{});
             else if (p.mix && ch >= p.split_chunk) issue_chunk(std::true_type{}, I0{}, I0{}, IH{}, IW{});  // skip source: TMA box
             else issue_chunk(std::false_type{}, I0{}, I0{}, IH{}, IW{});                                   // upsampled source: gather
           } else if (!RESIDENT) {
             const int par2 = (SPX == 2) ? ch / p.spx_cpp : 0;
-            const int nt_ch = (SPX == 2) ? ((par2 >> 1) + 1) * ((par2 & 1) + 1) : ((SPX && ch >= p.split_chunk) ? 4 : NT);
+            const int nt_ch = (SPX == 2) ? ((par2 >> 1) + 1) * ((par2 & 1) + 1) : ((SPX == 3 || (SPXP && ch >= p.split_chunk)) ? 4 : NT);
             for (int tap0 = 0; tap0 < nt_ch; tap0 += p.kpb) {
               mbar_wait_fast(bfull_bar(sb), phb);
               commit(bempty_bar(sb));
@@ -572,6 +601,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       const int oh = t.h0 + hi;
       const int ow0 = t.w0 + wi;
       const int col0 = t.n_tile * p.block_n;
+      // TMA coordinates of an output / residual box.  SPX == 3: the N tile is output parity (qh,qw) of a 2x larger tensor
+      // whose map walks every second pixel, so a box starts at pixel (2h + qh, 2w + qw), channel = column inside the tile
+      const int ec0 = (SPX == 3) ? 0 : col0;
+      auto ex = [&](int wpx) { return (SPX == 3) ? 2 * wpx + (t.n_tile & 1) : wpx; };
+      auto ey = [&](int hpx) { return (SPX == 3) ? 2 * hpx + (t.n_tile >> 1) : hpx; };
       const bool row_ok = oh < p.h;
       const long long pix0 = ((long long)t.img * p.h + oh) * p.w + ow0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (TG * bn);
@@ -583,7 +617,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       if (res_tma && lane == 0 && c_first * 4 < min(p.block_n, p.cout - col0)) {
         bulk_wait_read<0>();                 // the previous tile's last store has read the buffer out
         mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
-        tma_load_4d(stg, &tm_res, resbar(ewarp), col0 + c_first * 4, t.w0 + g_first * kHaloTW, t.h0 + q * 4, t.img);
+        tma_load_4d(stg, &tm_res, resbar(ewarp), ec0 + c_first * 4, ex(t.w0 + g_first * kHaloTW), ey(t.h0 + q * 4), t.img);
       }
 
       if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> nacc_log2) & 1u);
@@ -664,8 +698,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               if (RES && !TMA) {
                 r0[b] = make_uint4(0, 0, 0, 0); r1[b] = make_uint4(0, 0, 0, 0);
                 if (row_ok && (ow0 + g * kHaloTW < p.w)) {
-                  r0[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c);
-                  r1[b] = *reinterpret_cast<const uint4*>(rbase + g * rstep + c + 8);
+                  const __nv_bfloat16* rsrc = rbase + g * rstep + c;
+                  if (SHUF) {            // the residual lives at the shuffled output position
+                    const int par = (col0 + c) / p.shuffle, co = col0 + c - par * p.shuffle;
+                    const long long hp = ((long long)(t.img * 2 * p.h + 2 * oh + (par >> 1)) * (2 * p.w) +
+                                          2 * (ow0 + g * kHaloTW) + (par & 1));
+                    rsrc = p.res + hp * p.res_pitch + co;
+                  }
+                  r0[b] = *reinterpret_cast<const uint4*>(rsrc);
+                  r1[b] = *reinterpret_cast<const uint4*>(rsrc + 8);
                 }
               }
             };
@@ -724,7 +765,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                      tma_store_4d(&tm_out, stg, col0 + cg0, t.w0 + g * kHaloTW, t.h0 + q * 4, t.img);
+                      tma_store_4d(&tm_out, stg, ec0 + cg0, ex(t.w0 + g * kHaloTW), ey(t.h0 + q * 4), t.img);
                       bulk_commit();
                       if (RES) {           // next unit of this tile: its residual box, once the store has read the buffer
                         const int gi_n = (n >> LOG2_JN) + 1;
@@ -733,7 +774,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                         if (cg_n < ncols) {
                           bulk_wait_read<0>();
                           mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
-                          tma_load_4d(stg, &tm_res, resbar(ewarp), col0 + cg_n, t.w0 + g_n * kHaloTW, t.h0 + q * 4, t.img);
+                          tma_load_4d(stg, &tm_res, resbar(ewarp), ec0 + cg_n, ex(t.w0 + g_n * kHaloTW), ey(t.h0 + q * 4), t.img);
                         }
                       }
                     }
@@ -755,7 +796,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         };
         using T_ = std::true_type; using F_ = std::false_type;
         if (tma_out) { if (p.res) run_items(T_{}, T_{}, F_{}); else run_items(T_{}, F_{}, F_{}); }
-        else if (p.shuffle) run_items(F_{}, F_{}, T_{});
+        else if (p.shuffle) { if (p.res) run_items(F_{}, T_{}, T_{}); else run_items(F_{}, F_{}, T_{}); }
         else if (p.res) run_items(F_{}, T_{}, F_{});
         else run_items(F_{}, F_{}, F_{});
       }
@@ -798,7 +839,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               if (ch < p.split_chunk)
                 tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase * p.a_scale,
                             hbase * p.a_scale, t.img);
-              else if (SPX) {
+              else if (SPXP) {
                 // parity plane (ph,pw) of the full-resolution skip source: halo block b is pixel 2b + parity
                 const int e = ch - p.split_chunk, par = e / p.spx_cpp, cc = e - par * p.spx_cpp;
                 tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), cc * KC, 2 * wbase + (par & 1),

@@ -503,7 +503,8 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   //   L2     : halo(tg)*cin*2 + (weights streamed ? bn*K*2 : 0) bytes per tile; ~64 B/clk per SM, 6300 B/clk chip
   // epilogue staging for TMA tensor stores (8 warps x 32 rows x 128 B): outputs with a multiple of 64 channels
   static const bool ep_tma_enabled = []{ const char* e = getenv("UWM_EP_TMA"); return !(e && e[0] == '0'); }();
-  const bool ep_tma = ep_tma_enabled && !s.head && !s.shuffle && (s.cout_pad % 64 == 0);
+  const bool par_tiles_early = s.shuffle && !s.x2 && s.cout_pad > 256;      // sub-pixel conv, one N tile per parity
+  const bool ep_tma = ep_tma_enabled && !s.head && (!s.shuffle || par_tiles_early) && (s.cout_pad % 64 == 0);
   const size_t stg_bytes = ep_tma ? (size_t)8 * 32 * 128 + 1024 : 0;
   const size_t kBudget = 206u * 1024u - stg_bytes; // rings + resident weights (barriers/alignment slack on top)
   const int sms = num_sms();
@@ -516,9 +517,15 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     const size_t pl = ((size_t)cps * halo_plane_bytes(tg, kh, kw) + 1023) & ~(size_t)1023;
     return std::max(sw, pl);          // a gathered stage (planes) or a TMA box of the skip source (swizzled rows)
   };
+  // sub-pixel conv with more than 256 GEMM columns: one N tile per output parity, 4 of the 9 taps each (SPX == 3)
+  const bool par_tiles = s.shuffle && !s.x2 && s.cout_pad > 256;
+  if (par_tiles && (kc != 64 || (s.shuffle != 128 && s.shuffle != 256) || s.cout_pad != 4 * s.shuffle || !a_tma))
+    return fail(UWM_EINVAL, "sub-pixel conv: cout=%d needs cout in {128, 256} and cin a multiple of 64", s.shuffle);
+  if (s.shuffle && s.res && !par_tiles) return fail(UWM_EINVAL, "sub-pixel conv: residual only with cout in {128, 256}");
   struct Cand { int bn, tg; bool resident; double cost; } best = {0, 0, false, 1e30};
   std::vector<int> bns;
-  if (s.cout_pad <= 64) bns.push_back(s.cout_pad);
+  if (par_tiles) bns.push_back(s.shuffle);
+  else if (s.cout_pad <= 64) bns.push_back(s.cout_pad);
   else for (int c : {256, 128, 64}) if (s.cout_pad % c == 0) bns.push_back(c);
   if (bns.empty()) { int b = std::min(s.cout_pad, 256); while (s.cout_pad % b) b -= 16; bns.push_back(b); }
   const int w8 = (s.w + kHaloTW - 1) / kHaloTW;
@@ -533,7 +540,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const size_t a_stage = a_stage_of(tg);
       const size_t b_slice = ((size_t)bn * kc * 2 + 1023) & ~(size_t)1023;
       const int n_tiles = s.cout_pad / bn;
-      const bool resident = (n_tiles == 1) && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
+      const bool resident = (n_tiles == 1) && !par_tiles && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
       if (!resident && (tg > 2 || 2 * b_slice + 2 * a_stage > kBudget)) break;   // streamed kernels: TG 1, 2
       if (s.s2d && (!resident || tg > 4 || !a_tma)) break;         // S2D: resident weights, TG 1, 2, 4, TMA-fed
       if (s.s2d && s.head && tg > 2) break;                        // head: 79 KB stages at TG 4 leave a 2-deep ring (measured slower)
@@ -558,6 +565,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   if (!best.bn) return fail(UWM_EINVAL, "halo conv: no tile fits shared memory (cin=%d cout=%d)", cin_total, s.cout_pad);
   const int bn = best.bn, tg = best.tg;
   L->kh = kh; L->kw = kw; L->kc = kc; L->tg = tg; L->resident = best.resident ? 1 : 0; L->a_tma = a_tma ? 1 : 0;
+  if (par_tiles) L->spx = 3;
   a.tiles_w = (s.w + kHaloTW * tg - 1) / (kHaloTW * tg);
   a.tiles_h = (s.h + kHaloTH - 1) / kHaloTH;
   const int m_tiles = a.tiles_w * a.tiles_h * s.n;
@@ -582,7 +590,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   static const int cg2_mode = []{ const char* e = getenv("UWM_CG2"); return e ? atoi(e) : 1; }();
   const double cg2_bytes_per_clk = ((double)halo_npix(tg, kh, kw) * cin_total * 2 + (double)bn * nk * kc * 2) /
                                    ((double)tg * nk * (kc / 16) * (bn >= 256 ? 128.0 : 32.0 + bn / 4.0));
-  const bool cg2 = cg2_mode > 0 && (cg2_mode == 2 || cg2_bytes_per_clk > 50.0) && !best.resident && a_tma && !s.x2 &&
+  const bool cg2 = cg2_mode > 0 && (cg2_mode == 2 || cg2_bytes_per_clk > 50.0) && !best.resident && a_tma && !s.x2 && !par_tiles &&
                    !s.s2d && !s.head && !s.shuffle && !s.in_stride2 && kc == 64 && kh == 3 && kw == 3 &&
                    (m_tiles % 2 == 0) && bn % 32 == 0 && a.total_tiles >= 2;
   L->cg2 = cg2 ? 1 : 0;
@@ -606,6 +614,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       kpb = d;
       if (d * mma_cycles >= 512) break;
     }
+    if (par_tiles) kpb = 1;                       // the N tile's four taps are not contiguous in K
     a.kpb = kpb;
     const size_t b_stage = (size_t)kpb * a.b_slice_bytes;
     const size_t a_keep = std::min(a_min, kBudget - 2 * b_stage);
@@ -630,7 +639,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   { static const bool mix_on = []{ const char* e = getenv("UWM_MIX"); return !(e && e[0] == '0'); }();
     a.mix = (!a_tma && s.x2 && mix_on) ? 1 : 0; }
   { const char* e = getenv("UWM_TRACE_KH"); if (e && atoi(e) != kh) a.trace = nullptr; }   // bench-only: trace one filter shape
-  a.shuffle = s.shuffle;
+  a.shuffle = (par_tiles && ep_tma) ? 0 : s.shuffle;      // the strided TMA view does the pixel shuffle
   a.ep_tma = ep_tma ? 1 : 0; a.ep_cols = ep_tma ? 64 : 16;
   { const char* e = getenv("UWM_VERBOSE");
     if (e && e[0] == '1')
@@ -656,11 +665,13 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(wgt) -> %d (k=%llu cout=%d)", (int)r, (unsigned long long)ktot, s.cout_pad);
   if (ep_tma) {
     // output view [n][h][w][cout] (pixel pitch out_pitch): boxes of 64 channels x 8 x 4 pixels, 128B-swizzled in smem
-    cuuint64_t odims[4] = {(cuuint64_t)s.cout, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
-    cuuint64_t ostr[3] = {(cuuint64_t)s.out_pitch * 2, (cuuint64_t)s.w * s.out_pitch * 2,
-                          (cuuint64_t)s.h * s.w * s.out_pitch * 2};
-    cuuint32_t obox[4] = {64, (cuuint32_t)kHaloTW, 4, 1};
-    cuuint32_t oest[4] = {1, 1, 1, 1};
+    // par_tiles: the output is [n][2h][2w][shuffle]; a box covers every second pixel of every second row (one parity)
+    const int osc = par_tiles ? 2 : 1;
+    const cuuint64_t ow_ = (cuuint64_t)s.w * osc, oh_ = (cuuint64_t)s.h * osc;
+    cuuint64_t odims[4] = {(cuuint64_t)(par_tiles ? s.shuffle : s.cout), ow_, oh_, (cuuint64_t)s.n};
+    cuuint64_t ostr[3] = {(cuuint64_t)s.out_pitch * 2, ow_ * s.out_pitch * 2, oh_ * ow_ * s.out_pitch * 2};
+    cuuint32_t obox[4] = {64, (cuuint32_t)(kHaloTW * osc), (cuuint32_t)(4 * osc), 1};
+    cuuint32_t oest[4] = {1, (cuuint32_t)osc, (cuuint32_t)osc, 1};
     r = enc(&L->tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s.out, odims, ostr, obox, oest, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -668,8 +679,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
                   s.n, s.out_pitch);
     L->tm_res = L->tm_out;
     if (s.res) {              // residual view with the same boxes (added in place in the staging buffer)
-      cuuint64_t rstr[3] = {(cuuint64_t)s.res_pitch * 2, (cuuint64_t)s.w * s.res_pitch * 2,
-                            (cuuint64_t)s.h * s.w * s.res_pitch * 2};
+      cuuint64_t rstr[3] = {(cuuint64_t)s.res_pitch * 2, ow_ * s.res_pitch * 2, oh_ * ow_ * s.res_pitch * 2};
       r = enc(&L->tm_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(s.res), odims, rstr, obox, oest,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -902,6 +912,18 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   }
   UWM_HALO_SPX(1) UWM_HALO_SPX(2)
 #undef UWM_HALO_SPX
+  // sub-pixel convs with one N tile per output parity (SPX == 3): streamed weights, TMA-fed
+#define UWM_HALO_PAR(TG)                                                                                          \
+  if (!L) {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, false, true, 3>,                                 \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
+  } else if (L->spx == 3 && L->tg == TG && !L->resident) {                                                        \
+    launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, 3>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,     \
+               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
+    return UWM_OK;                                                                                                \
+  }
+  UWM_HALO_PAR(1) UWM_HALO_PAR(2)
+#undef UWM_HALO_PAR
   // stride-2 3x3 convs over parity planes (SPX == 2): 2x2 block halo
 #define UWM_HALO_S2(TG)                                                                                           \
   if (!L) {                                                                                                       \
@@ -998,6 +1020,26 @@ extern "C" int uwm_conv2d_upcat_nhwc_bf16(const void* d_x, int n, int h, int w, 
   s.wgt = d_wgt; s.bias = d_bias; s.cout = cout; s.cout_pad = cout;
   taps_rect(&s, kh, kw, pad);
   s.stride = 1; s.h_out = s.h; s.w_out = s.w;
+  s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
+  ConvLaunch L;
+  int rc = build_halo(s, &L);
+  if (rc) return rc;
+  return launch_conv(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uwm_conv2d_up2x_shuffle_res_nhwc_bf16(const void* d_x, int n, int h, int w, int cin, int x_pitch,
+                                                     const void* d_wgt, const float* d_bias, int cout,
+                                                     const void* d_res, int res_pitch, int relu, void* d_y, int y_pitch,
+                                                     void* stream) {
+  if (!d_x || !d_wgt || !d_bias || !d_y) return fail(UWM_EINVAL, "conv2d_up2x_shuffle: null pointer");
+  if (cout % 16 || (4 * cout > 256 && cout != 128 && cout != 256))
+    return fail(UWM_EINVAL, "conv2d_up2x_shuffle: cout=%d must be a multiple of 16 up to 64, or 128 / 256", cout);
+  ConvSpec s;
+  s.x = d_x; s.n = n; s.h = h; s.w = w; s.cin = cin; s.x_pitch = x_pitch;
+  s.wgt = d_wgt; s.bias = d_bias; s.cout = 4 * cout; s.cout_pad = 4 * cout; s.shuffle = cout;
+  taps_rect(&s, 3, 3, 1);
+  s.stride = 1; s.h_out = h; s.w_out = w;
+  s.res = d_res; s.res_pitch = res_pitch;
   s.relu = relu; s.out = d_y; s.out_pitch = y_pitch;
   ConvLaunch L;
   int rc = build_halo(s, &L);
@@ -1413,9 +1455,27 @@ static int build_plan(uwm_model* m) {
     const bool spx = cs[i] > 0 && spx_on && subpixel_enabled() && 4 * dec[i] <= 256 && dec[i] % 16 == 0 &&
                      cx[i] % 64 == 0 && cs[i] % 64 == 0;
     const bool subpixel = ((cs[i] == 0) && subpixel_enabled() && 4 * dec[i] <= 256) || spx;
-    int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0, false, subpixel,
-                       spx ? cs[i] : 0);
-    add_conv(m, l1, x, t1, nullptr, false, /*up=*/true, cs[i] ? &skip[i] : nullptr);
+    // Blocks whose sub-pixel form would need more than 256 GEMM columns (default decoder: blocks 0 and 1) run conv1 as
+    // two launches: the skip half as an ordinary 3x3 conv into a partial-sum tensor (bias folded here, no ReLU), then
+    // the upsampled half as a sub-pixel conv with one N tile per output parity (4 of 9 taps each) whose pixel-shuffle
+    // epilogue adds that partial sum and applies the ReLU.  The partial sum is stored in bf16 (one extra rounding).
+    static const bool split_on = []{ const char* e = getenv("UWM_SPLIT_UPCAT"); return !(e && e[0] == '0'); }();
+    const bool split = cs[i] > 0 && !spx && split_on && subpixel_enabled() && (dec[i] == 128 || dec[i] == 256) &&
+                       cx[i] % 64 == 0 && cs[i] % 64 == 0;
+    if (split) {
+      TRef part = m->dense(bh, bw, dec[i]);
+      int la = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cs[i], dec[i], 3, 1, 1, /*relu=*/0, 0);
+      m->layers[la].d.pack = UWM_PACK_TAPS_SKIP_PART; m->layers[la].d.cin_skip = cs[i];
+      add_conv(m, la, skip[i], part, nullptr);
+      int lb = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i], dec[i], 3, 1, 1, /*relu=*/1, /*has_res=*/1, false,
+                         /*shuffle=*/true);
+      m->layers[lb].d.pack = UWM_PACK_UP2X_SHUFFLE_X_PART; m->layers[lb].d.cin_skip = cs[i];
+      add_conv(m, lb, x, t1, &part, false, /*up=*/true, nullptr);
+    } else {
+      int l1 = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i] + cs[i], dec[i], 3, 1, 1, 1, 0, false, subpixel,
+                         spx ? cs[i] : 0);
+      add_conv(m, l1, x, t1, nullptr, false, /*up=*/true, cs[i] ? &skip[i] : nullptr);
+    }
     TRef t2 = s2d ? m->dense(bh / 2, bw / 2, 4 * dec[i]) : m->dense(bh, bw, dec[i]);
     t2.s2d = s2d;
     int l2 = add_layer(m, pre + ".conv2.0", pre + ".conv2.1", dec[i], dec[i], 3, 1, 1, 1, 0, false, false, 0, s2d);

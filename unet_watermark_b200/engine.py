@@ -76,6 +76,12 @@ class Engine:
             if d.pack == _lib.PACK_STEM_S2D:
                 wp = packing.pack_stem_s2d(w, d.cout_pad)
                 bp = packing.pad_bias(b, d.cout_pad)
+            elif d.pack == _lib.PACK_TAPS_SKIP_PART:
+                wp = packing.pack_taps(w[:, w.shape[1] - d.cin_skip:], d.cout_pad)      # skip half of a two-launch conv1
+                bp = packing.pad_bias(b, d.cout_pad)
+            elif d.pack == _lib.PACK_UP2X_SHUFFLE_X_PART:
+                wp = packing.pack_up2x_shuffle(w[:, :w.shape[1] - d.cin_skip])        # upsampled half, bias already added
+                bp = torch.zeros(d.cout_pad, dtype=torch.float32)
             elif d.pack == _lib.PACK_S2_PLANES:
                 wp = packing.pack_s2_planes(w)                              # stride-2 conv over parity planes
                 bp = packing.pad_bias(b, d.cout_pad)

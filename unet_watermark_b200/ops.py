@@ -91,6 +91,26 @@ def conv2d_up2x_shuffle(x: torch.Tensor, w_shuffle: torch.Tensor, bias4: torch.T
     return out
 
 
+def conv2d_up2x_shuffle_res(x: torch.Tensor, w_shuffle: torch.Tensor, bias4: torch.Tensor,
+                            residual: Optional[torch.Tensor] = None, relu: bool = True,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(conv3x3(nearest_up2x(x)) + bias + residual) as a sub-pixel conv; Cout up to 64, or 128 / 256 (one N tile per
+    output parity).  residual: [N,2h,2w,Cout] bf16 or None."""
+    _require_cuda(x, w_shuffle, bias4, residual, out)
+    lib = _lib.load()
+    n, h, w, cin = x.shape
+    cout = w_shuffle.shape[0] // 4
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=x.device)
+    rc = lib.uwm_conv2d_up2x_shuffle_res_nhwc_bf16(x.data_ptr(), n, h, w, cin, _pitch(x), w_shuffle.data_ptr(),
+                                                   bias4.data_ptr(), cout,
+                                                   residual.data_ptr() if residual is not None else None,
+                                                   _pitch(residual) if residual is not None else 0, int(relu),
+                                                   out.data_ptr(), _pitch(out), _stream())
+    _lib.check(rc, "uwm_conv2d_up2x_shuffle_res_nhwc_bf16")
+    return out
+
+
 def conv2d_upcat_subpixel(x: torch.Tensor, skip: torch.Tensor, w_spx: torch.Tensor, bias4: torch.Tensor,
                           relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """conv3x3(concat(nearest_up2x(x), skip)) (+bias)(+ReLU) as a sub-pixel conv on x's grid.
