@@ -25,6 +25,9 @@ def main():
     for name, n, h, w, cx, cs, cout, up in SHAPES:
         if args.filter not in name:
             continue
+        if up == "par" or (up in ("s2d", "s2dhead") and "gap" in __file__):
+            print(f"{name}: not driven by this tool (use tools/gpu_conv_bench.py)")
+            continue
         x = torch.randn(n, h, w, cx, device=dev).to(torch.bfloat16)
         ho, wo = (2 * h, 2 * w) if up else (h, w)
         skip = torch.randn(n, ho, wo, cs, device=dev).to(torch.bfloat16) if cs else None
