@@ -34,8 +34,31 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec UNet-ResNet34 512x512 bf16 mask inference"
 UNIT = "images/s"
+# BASELINE.json configs (1-based, as VERDICT/SURVEY number them).  The default line is configs[1] = "config 2".
+CONFIGS = {
+    2: dict(encoder="resnet34", size=512, batch=16, scaling="weak", metric=METRIC,
+            workload="configs[1]: smp Unet resnet34, 512x512, batch 16 per GPU, bf16 inference, sigmoid+threshold uint8 mask"),
+    3: dict(encoder="resnet34", size=1024, batch=64, scaling="strong",
+            metric="images/sec UNet-ResNet34 1024x1024 bf16 mask inference",
+            workload="configs[2]: smp Unet resnet34, 1024x1024, batch 64 TOTAL split data-parallel over the GPUs "
+                     "(64/N images per GPU), bf16 inference, sigmoid+threshold uint8 mask"),
+    4: dict(encoder="resnet50", size=768, batch=32, scaling="weak",
+            metric="images/sec UNet-ResNet50 768x768 bf16 mask inference",
+            workload="configs[3]: smp Unet resnet50, 768x768, batch 32 per GPU, bf16 inference, sigmoid+threshold uint8 mask"),
+}
 ENCODER, SIZE, BATCH = "resnet34", 512, 16
-WORKLOAD = "configs[1]: smp Unet resnet34, 512x512, batch 16 per GPU, bf16 inference, sigmoid+threshold uint8 mask"
+WORKLOAD = CONFIGS[2]["workload"]
+SCALING = "weak"
+
+
+def select_config(n: int, world: int):
+    """Bind the module-level workload constants to BASELINE config n (per-GPU batch for the strong-scaling config 3)."""
+    global ENCODER, SIZE, BATCH, WORKLOAD, METRIC, SCALING
+    c = CONFIGS[n]
+    ENCODER, SIZE, WORKLOAD, METRIC, SCALING = c["encoder"], c["size"], c["workload"], c["metric"], c["scaling"]
+    BATCH = c["batch"] // world if c["scaling"] == "strong" else c["batch"]
+    if BATCH < 1:
+        raise SystemExit(f"config {n}: {c['batch']} images do not split over {world} GPUs")
 
 
 def load_peaks():
@@ -118,15 +141,56 @@ def cpu_reference_run(steps: int, warmup: int, images_per_step: int):
     return images_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def gpu_control_run(dev, u8_batch, steps: int):
+    """Same-GPU control: the oracle module (torchvision ResNet + restated smp decoder) run by stock torch as bf16
+    channels_last - i.e. cuDNN / cuBLAS kernels - on the same uint8 inputs, normalisation and threshold included.
+    Not part of the product path; it is what `model.to('cuda').to(bfloat16)` of the reference would run."""
+    import torch
+    from oracle import unet_oracle as O
+    try:
+        torch.backends.cudnn.benchmark = True
+        ref = O.build(ENCODER, seed=0, random_bn=True).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        mean = torch.tensor(O.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1) * 255.0
+        inv = 1.0 / (torch.tensor(O.IMAGENET_STD, device=dev).view(1, 3, 1, 1) * 255.0)
+        n = u8_batch.shape[0]
+        chunk = n if n * SIZE * SIZE <= 16 * 1024 * 1024 else max(1, (16 * 1024 * 1024) // (SIZE * SIZE))
+
+        def step():
+            out = []
+            for i in range(0, n, chunk):
+                x = ((u8_batch[i:i + chunk].permute(0, 3, 1, 2).float() - mean) * inv).to(torch.bfloat16)
+                x = x.contiguous(memory_format=torch.channels_last)
+                out.append((ref(x)[:, 0] > 0).to(torch.uint8) * 255)
+            return out
+        with torch.no_grad():
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                step()
+            b.record()
+            torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / steps
+        del ref
+        torch.cuda.empty_cache()
+        return {"value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "images_per_step": n,
+                "impl": "stock torch bf16 channels_last (cuDNN), oracle module, same GPU, same uint8 inputs, eager"}
+    except Exception as e:  # noqa: BLE001 - the control must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    per_step = 2
+    select_config(args.config, int(os.environ.get("WORLD_SIZE", "1")))
+    per_step = 2 if SIZE <= 512 else 1
     v, ms, cores = cpu_reference_run(args.steps, max(args.warmup, 1), per_step)
     sample = f"{per_step} of {BATCH} images per step, fp32, oracle port of the reference CPU path, {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -146,6 +210,19 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    select_config(args.config, world)
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one disjoint CPU set per rank: the launch thread and the pinned-memory copies of eight ranks otherwise
+        # migrate over the same cores (r01: e2e scaled 0.974 at 8 GPUs while the device-resident value scaled 0.992)
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            mine = cpus[local * per:(local + 1) * per] or cpus
+            os.sched_setaffinity(0, mine)
+            affinity = [mine[0], mine[-1]]
+        except OSError:
+            affinity = None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -168,8 +245,9 @@ def run_ours(args):
             m.running_var.uniform_(0.7, 1.3, generator=g)
     model = model.to(dev).eval()
 
-    # synthetic uint8 RGB batches; the rotating pool (12.6 MB each) is larger than the 126 MB L2
-    n_pool = 12
+    # synthetic uint8 RGB batches; the rotating pool is larger than the 126 MB L2
+    batch_bytes = BATCH * SIZE * SIZE * 3
+    n_pool = max(2, min(12, -(-160_000_000 // batch_bytes)))
     gi = torch.Generator().manual_seed(100 + rank)
     host_pool = [torch.randint(0, 256, (BATCH, SIZE, SIZE, 3), dtype=torch.uint8, generator=gi).pin_memory()
                  for _ in range(n_pool)]
@@ -211,27 +289,41 @@ def run_ours(args):
     out_hosts = [torch.empty(BATCH, SIZE, SIZE, dtype=torch.uint8).pin_memory() for _ in range(2)]
     s_h2d, s_cmp, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
-    def e2e_loop(nsteps):
+    stage_ev = []              # per step: (h2d start, h2d end, compute start, compute end, d2h start, d2h end)
+
+    def e2e_loop(nsteps, timed=False):
         up = [None, None]      # upload finished (per buffer)
         done = [None, None]    # compute finished: input buffer reusable, mask ready
         down = [None, None]    # download finished: mask buffer / host buffer reusable
         for i in range(nsteps):
             b = i % 2
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timed else None
             with torch.cuda.stream(s_h2d):
                 if done[b] is not None:
                     s_h2d.wait_event(done[b])
+                if timed:
+                    ev[0].record(s_h2d)
                 in_bufs[b].copy_(host_pool[i % n_pool], non_blocking=True)          # H2D of this step's inputs
-                up[b] = torch.cuda.Event(); up[b].record(s_h2d)
+                up[b] = ev[1] if timed else torch.cuda.Event()
+                up[b].record(s_h2d)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(up[b])
                 if down[b] is not None:
                     s_cmp.wait_event(down[b])
+                if timed:
+                    ev[2].record(s_cmp)
                 model.predict_mask(in_bufs[b], 0.5, out=mask_bufs[b])
-                done[b] = torch.cuda.Event(); done[b].record(s_cmp)
+                done[b] = ev[3] if timed else torch.cuda.Event()
+                done[b].record(s_cmp)
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(done[b])
+                if timed:
+                    ev[4].record(s_d2h)
                 out_hosts[b].copy_(mask_bufs[b], non_blocking=True)                  # D2H of this step's masks
-                down[b] = torch.cuda.Event(); down[b].record(s_d2h)
+                down[b] = ev[5] if timed else torch.cuda.Event()
+                down[b].record(s_d2h)
+            if timed:
+                stage_ev.append(ev)
         for s_ in (s_h2d, s_cmp, s_d2h):
             s_.synchronize()
 
@@ -241,16 +333,44 @@ def run_ours(args):
     e2.record()
     for s_ in (s_h2d, s_cmp, s_d2h):
         s_.wait_stream(torch.cuda.current_stream())
-    e2e_loop(args.steps)
+    e2e_loop(args.steps, timed=True)
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
     e2e_checksum = int(out_hosts[(args.steps - 1) % 2].sum().item())
+    # per-stage device time of one step on its own stream (mean over the timed steps): names the exposed stage
+    stage_ms = [sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for ev in stage_ev) / max(len(stage_ev), 1) for k in range(3)]
+
+    # ---- sustained leg: >= 3 s of back-to-back graph replays (device-resident), own clock record --------
+    sustained = None
+    if not args.no_sustained:
+        est = max(ms_total / args.steps, 1e-3)
+        n_sus = int(min(max(3000.0 / est, args.steps), 200000))
+        sync_all()
+        samp2 = ClockSampler(local)
+        samp2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_sus):
+            model.predict_mask(dev_pool[i % n_pool], 0.5, out=mask_bufs[i % 2])
+        s1.record()
+        sync_all()
+        ms_sus = s0.elapsed_time(s1)
+        sustained = {"steps": n_sus, "ms_total": ms_sus, "ms_per_step": ms_sus / n_sus, "clocks": samp2.stop()}
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, sustained["ms_total"] if sustained else 0.0] + stage_ms, device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
+        if sustained:
+            sustained["ms_total"] = float(t[2]); sustained["ms_per_step"] = float(t[2]) / sustained["steps"]
+        stage_ms = [float(v) for v in t[3:6]]
+
+    # ---- GPU control: the oracle module as stock torch bf16 channels_last (cuDNN) on the same GPU ---------
+    gpu_control = None
+    if rank == 0 and not args.no_gpu_control:
+        gpu_control = gpu_control_run(dev, dev_pool[0], steps=max(3, min(args.steps, 10)))
 
     # ---- roofline of the dominant kernels (the tcgen05 convs) -------------------------------
     conv_ms = conv_flops = other_ms = 0.0
@@ -281,7 +401,7 @@ def run_ours(args):
     achieved_eager = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
+    if args.config == 2 and os.path.exists(tp):
         try:
             with open(tp) as f:
                 traffic = json.load(f).get("conv_dram_bytes_per_step")
@@ -290,6 +410,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "conv_halo_kernel (tcgen05 implicit-GEMM convs, all conv launches of the step)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                "traffic_static": True if traffic is not None else None,   # read from profiles/roofline_traffic.json (ncu capture of this build), not measured in this run
                 "peak_source": peaks["source"] + ", burst figure",
                 "how": f"algorithmic conv FLOPs of one step ({flops_step / 1e12:.4f} TFLOP, {n_conv} conv launches) / "
                        f"(timed ms_per_step x conv share {conv_share:.4f}); share = CUDA-event time of the conv launches / "
@@ -305,8 +426,9 @@ def run_ours(args):
         e2e_v = world * BATCH * args.steps / (ms_e2e * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "encoder": ENCODER, "image": [SIZE, SIZE], "batch_per_gpu": BATCH,
+                "scaling": SCALING, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "baseline_config": args.config, "encoder": ENCODER, "image": [SIZE, SIZE],
+                           "batch_per_gpu": BATCH, "cpu_affinity": affinity,
                            "global_batch": BATCH * world, "parallelism": f"dp{world}",
                            "weights": "random-init (seeded), BatchNorm folded",
                            "l2": f"inputs rotate through {n_pool} batches ({n_pool * BATCH * SIZE * SIZE * 3 / 1e6:.0f} MB) > 126 MB L2; "
@@ -318,12 +440,25 @@ def run_ours(args):
                         "d2h_bytes_per_step": world * BATCH * SIZE * SIZE, "ms_per_step": ms_e2e / args.steps,
                         "api": "pinned host uint8 NHWC -> H2D -> Unet.predict_mask(x, 0.5, out=) -> D2H -> pinned host uint8 masks; "
                                "double-buffered over H2D / compute / D2H streams",
+                        "stage_ms": {"h2d": stage_ms[0], "compute": stage_ms[1], "d2h": stage_ms[2],
+                                     "how": "CUDA events around each stage on its own stream, mean per step, max over ranks"},
                         "mask_checksum": e2e_checksum},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "mask_checksum": checksum}
+        if sustained:
+            v_sus = world * BATCH * sustained["steps"] / (sustained["ms_total"] * 1e-3)
+            tf_sus = v_sus * eng.flops_per_image / 1e12 / world
+            sustained.update({"value": v_sus, "unit": UNIT, "tflops_per_gpu": tf_sus,
+                              "frac_of_bf16_sustained_peak": tf_sus / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None,
+                              "frac_of_bf16_burst_peak": tf_sus / peaks["bf16_tflops"],
+                              "peak_sustained_tflops": peaks["bf16_tflops_sustained"]})
+            line["sustained"] = sustained
+        if gpu_control:
+            line["gpu_control"] = gpu_control
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores = cpu_reference_run(steps=5, warmup=1, images_per_step=2)
+            per = 2 if SIZE <= 512 else 1
+            v, ms, cores = cpu_reference_run(steps=5 if SIZE <= 512 else 3, warmup=1, images_per_step=per)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "5 timed steps x 2 images (of the 16-image batch), fp32, oracle port of "
+                                    "sample": f"timed steps x {per} images (of the {BATCH}-image batch), fp32, oracle port of "
                                               "the reference CPU path, all host threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -339,6 +474,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-control", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--config", type=int, choices=sorted(CONFIGS), default=2,
+                    help="BASELINE.json config (1-based): 2 = r34 512 B16 (default line), 3 = r34 1024 B64 split over the GPUs, "
+                         "4 = r50 768 B32")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -241,6 +241,10 @@ int    uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int batch,
                          char* names, float* ms, double* flops, double* bytes, int n_max,
                          void* stream);
 
+/* ---- bench tools: exported only by the tools build of the library (-DUWM_BENCH_TOOLS; python -m
+ * unet_watermark_b200.build --tools -> lib/libuwm_b200_tools.so).  The product library has none of these, nor the
+ * UWM_DBG pipeline-isolation switches. ---- */
+#ifdef UWM_BENCH_TOOLS
 /* Sizing micro-benchmark (tools/gpu_microbench.py), not on the product path: each of `blocks` CTAs issues
  * `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16) and writes its clock64() delta to d_cycles. */
 int    uwm_debug_mma_rate(int n, int iters, int distinct_stages, int mode, int blocks, long long* d_cycles,
@@ -255,6 +259,8 @@ int    uwm_debug_prim_cost(int which, int iters, long long* d_out, void* stream)
 
 /* Sizing micro-benchmark: mbarrier ping-pong between two warps, cycles for `iters` round trips. */
 int    uwm_debug_handshake(int iters, int variant, int blocks, long long* d_cycles, void* stream);
+
+#endif /* UWM_BENCH_TOOLS */
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "uwm.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#ifdef UWM_BENCH_TOOLS.*?#endif", "", src, flags=re.S)      # tools build only (checked below)
     return sorted(set(re.findall(r"\b(uwm_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -36,6 +37,20 @@ def test_binding_table_matches_header():
     assert sorted(_lib.SIGNATURES) == header_symbols()
     lib = _lib.load()
     assert lib.uwm_abi_version() == 1
+
+
+def test_product_library_has_no_bench_tools():
+    """uwm_debug_* and the UWM_DBG switches live only in the tools build (-DUWM_BENCH_TOOLS)."""
+    src = open(os.path.join(ROOT, "include", "uwm.h")).read()
+    tools = re.search(r"#ifdef UWM_BENCH_TOOLS(.*?)#endif", src, flags=re.S).group(1)
+    declared = sorted(set(re.findall(r"\b(uwm_debug_[a-z0-9_]+)\s*\(", tools)))
+    assert declared == sorted(_lib.TOOLS_SIGNATURES)
+    if os.path.basename(_lib.LIB_PATH) == "libuwm_b200.so":
+        lib = ctypes.CDLL(_lib.LIB_PATH)
+        for s in declared:
+            assert not hasattr(lib, s), f"{s} exported by the product library"
+        blob = open(_lib.LIB_PATH, "rb").read()
+        assert b"UWM_DBG" not in blob and b"UWM_TRACE_KH" not in blob
 
 
 def test_layer_desc_struct_matches_header_layout():

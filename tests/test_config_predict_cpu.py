@@ -79,6 +79,26 @@ def test_get_image_files_rules(tmp_path):
     assert len(pred._get_image_files(str(inp), str(out), limit=2)) == 2
 
 
+def test_rank_partition_is_stable_when_other_ranks_already_wrote_masks(tmp_path):
+    """shard the full sorted list first, filter inside the shard; --limit picks the same subset on all ranks."""
+    inp, out = tmp_path / "in", tmp_path / "out"
+    inp.mkdir(); out.mkdir()
+    names = [f"img_{i:02d}.png" for i in range(10)]
+    for n in names:
+        (inp / n).write_bytes(b"x")
+    pred = object.__new__(P.WatermarkPredictor)
+    r0 = pred._get_image_files(str(inp), str(out), rank=0, world_size=2)
+    for f in r0[:3]:                                              # rank 0 is ahead: three of its masks exist already
+        (out / (os.path.splitext(os.path.basename(f))[0] + "_mask.png")).write_bytes(b"x")
+    r1 = pred._get_image_files(str(inp), str(out), rank=1, world_size=2)       # rank 1 lists the folder late
+    assert [os.path.basename(f) for f in r0] == names[0::2]
+    assert [os.path.basename(f) for f in r1] == names[1::2]      # unchanged by rank 0's progress
+    assert [os.path.basename(f) for f in pred._get_image_files(str(inp), str(out), rank=0, world_size=2)] == names[6::2]
+    a = pred._get_image_files(str(inp), None, limit=4, rank=0, world_size=2)
+    b = pred._get_image_files(str(inp), None, limit=4, rank=1, world_size=2)
+    assert len(a) + len(b) == 4 and not set(a) & set(b)
+
+
 def test_shard_for_rank_partitions():
     items = list(range(11))
     shards = [P.shard_for_rank(items, r, 4) for r in range(4)]
@@ -125,6 +145,7 @@ def test_two_rank_gloo_sharding_covers_every_image_once():
 def test_cli_surface():
     p = build_parser()
     a = p.parse_args(["predict", "--input", "x", "--output", "y", "--model", "m.pth", "--save-mask", "--limit", "3"])
-    assert (a.command, a.input, a.output, a.model, a.limit, a.no_sigmoid) == ("predict", "x", "y", "m.pth", 3, False)
-    a = p.parse_args(["predict", "--no-sigmoid", "--threshold", "0.3", "--batch-size", "4"])
-    assert a.no_sigmoid and a.threshold == 0.3 and a.batch_size == 4
+    assert (a.command, a.input, a.output, a.model, a.limit, a.sigmoid) == ("predict", "x", "y", "m.pth", 3, False)
+    a = p.parse_args(["predict", "--sigmoid", "--threshold", "0.3", "--batch-size", "4"])
+    assert a.sigmoid and a.threshold == 0.3 and a.batch_size == 4
+    assert p.parse_args(["predict", "--no-sigmoid"]).sigmoid is False      # compat flag, default convention

@@ -1,11 +1,15 @@
 """End-to-end parity of the B200 path against the oracle (through the reference-shaped Python seam, which
 calls the C ABI).
 
-Tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle), stated relative to
-the logit scale of the fixture:
-    max |d|  <= 8 % of max|logit|         mean |d| <= 5 % of std(logit)
-and against the bf16-emulating oracle (same quantisation points, so only fp32 summation order differs)
-the early, un-amplified tensors must agree to a bf16 ulp.
+Tolerances (bf16 activations / fp32 accumulation vs the fp32 oracle).  The yardstick is the
+bf16-EMULATED oracle (oracle.forward_bf16_emulated: the same network with the same quantisation points computed by
+stock torch on the CPU): its own distance from the fp32 oracle is what bf16 storage costs on this fixture, and the
+device path must stay within
+    mean |d| <= 1.3 x emulation's mean |d|        p99.9 |d| <= 1.3 x emulation's p99.9 |d|
+    max  |d| <= 1.5 x emulation's max |d|         (a single-sample statistic)
+of it (measured r01: 1.04 x / 1.13 x).  A coarse absolute gate (8 % of max|logit|, 5 % of std) stays as a backstop
+for fixtures where no emulation is computed.  Against the emulation itself the early, un-amplified tensors must
+agree to a bf16 ulp.
 """
 import os
 
@@ -31,10 +35,22 @@ def make_pair(enc, dev, seed=0, random_bn=True, dec=(256, 128, 64, 32, 16), acti
     return ref, m.to(dev).eval()
 
 
-def assert_close_to_oracle(y, y32):
+def assert_close_to_oracle(y, y32, yemu=None):
     d = (y - y32).abs()
     assert d.max() <= MAX_FRAC * y32.abs().max(), (d.max().item(), y32.abs().max().item())
     assert d.mean() <= MEAN_FRAC * y32.std(), (d.mean().item(), y32.std().item())
+    if yemu is not None:
+        de = (yemu - y32).abs()
+        q = lambda t: torch.quantile(t.flatten()[:4_000_000].float(), 0.999).item()      # noqa: E731
+        assert d.mean() <= 1.3 * de.mean() + 1e-4, ("mean", d.mean().item(), de.mean().item())
+        assert q(d) <= 1.3 * q(de) + 1e-3, ("p99.9", q(d), q(de))
+        assert d.max() <= 1.5 * de.max() + 1e-3, ("max", d.max().item(), de.max().item())
+
+
+def norm_u8(u8):
+    mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+    return (u8.cpu().permute(0, 3, 1, 2).float() / 255.0 - mean) / std
 
 
 @pytest.mark.parametrize("enc,size,batch", [("resnet34", (128, 128), 2), ("resnet34", (96, 160), 3),
@@ -48,10 +64,8 @@ def test_logits_match_oracle(enc, size, batch, cuda_device):
     y = m(x.to(cuda_device))
     assert _lib.load().uwm_kernel_launch_count() - before == m.engine(batch, *size).kernels_per_forward
     assert y.shape == y32.shape and y.dtype == torch.float32 and y.is_cuda
-    assert_close_to_oracle(y.cpu(), y32)
-    # and at least as close as stock bf16 emulation of the same network is to fp32
-    yemu = O.forward_bf16_emulated(ref, x)
-    assert (y.cpu() - y32).abs().mean() <= 1.5 * (yemu - y32).abs().mean() + 1e-3
+    # within 1.3x of what stock bf16 emulation of the same network loses against fp32
+    assert_close_to_oracle(y.cpu(), y32, O.forward_bf16_emulated(ref, x))
 
 
 def test_early_features_match_bf16_emulation_to_one_ulp(cuda_device, monkeypatch):
@@ -176,8 +190,93 @@ def test_full_size_properties_config2(cuda_device):
     assert torch.equal(lp, logits[perm]) and torch.equal(mp_, mask[perm])
     # batch-size independence: image 3 alone gives the same bits
     assert torch.equal(m.predict_mask(u8[3:4].contiguous(), 0.5, return_logits=True)[1], logits[3:4])
-    mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
-    x0 = (u8[:1].cpu().permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    x0 = norm_u8(u8[:1])
     with torch.no_grad():
-        assert_close_to_oracle(logits[:1].cpu(), ref(x0))
+        assert_close_to_oracle(logits[:1].cpu(), ref(x0), O.forward_bf16_emulated(ref, x0))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3 and 4 at their named sizes
+# ------------------------------------------------------------------------------------------------------------
+def _size_properties(m, ref, u8, check_image, cuda_device, monkeypatch=None):
+    """Size-independent properties + one image against the fp32 and the bf16-emulated oracle."""
+    b = u8.shape[0]
+    mask, logits = m.predict_mask(u8, 0.5, return_logits=True)
+    mask, logits = mask.clone(), logits.clone()
+    mask2, logits2 = m.predict_mask(u8, 0.5, return_logits=True)
+    assert torch.equal(mask, mask2) and torch.equal(logits, logits2)                       # deterministic
+    assert torch.equal(mask, (logits[:, 0] > 0).to(torch.uint8) * 255)                     # mask == thresholded logits
+    perm = torch.randperm(b, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    mp_, lp = m.predict_mask(u8[perm].contiguous(), 0.5, return_logits=True)
+    assert torch.equal(lp, logits[perm]) and torch.equal(mp_, mask[perm])                  # images are independent
+    i = check_image
+    assert torch.equal(m.predict_mask(u8[i:i + 1].contiguous(), 0.5, return_logits=True)[1], logits[i:i + 1])
+    x0 = norm_u8(u8[i:i + 1])
+    with torch.no_grad():
+        y32 = ref(x0)
+    yemu = O.forward_bf16_emulated(ref, x0)
+    assert_close_to_oracle(logits[i:i + 1].cpu(), y32, yemu)
+    agree = (mask[i].cpu() == O.binarize(y32[0, 0])).float().mean().item()
+    assert agree > 0.97, agree                                   # random-init net: no margin at the threshold (F10)
+    return logits
+
+
+def test_full_size_config3_r34_1024(cuda_device):
+    """BASELINE config 3 per-GPU shard: resnet34, 1024x1024, 8 images (64 over 8 GPUs)."""
+    ref, m = make_pair("resnet34", cuda_device)
+    u8 = O.image_like_u8(8, 1024, seed=21).to(cuda_device)
+    _size_properties(m, ref, u8, 5, cuda_device)
+
+
+def test_config3_named_features_vs_bf16_emulation_1024(cuda_device, monkeypatch):
+    """Per named feature at 1024x1024 (M = 1 M pixels per image) against the bf16-emulated oracle."""
+    monkeypatch.setenv("UWM_KEEP_ALL", "1")
+    ref, m = make_pair("resnet34", cuda_device, seed=4)
+    u8 = O.image_like_u8(2, 1024, seed=22).to(cuda_device)
+    m.predict_mask(u8, 0.5)
+    eng = m.engine(2, 1024, 1024)
+    _, feats = O.forward_bf16_emulated(ref, norm_u8(u8), return_features=True)
+    for name, frac in (("encoder.stem", 0.002), ("encoder.maxpool", 0.002), ("encoder.layer1", 0.004),
+                       ("encoder.layer2", 0.01), ("encoder.layer3", 0.02), ("encoder.layer4", 0.02),
+                       ("decoder.blocks.0", 0.02), ("decoder.blocks.1", 0.02), ("decoder.blocks.2", 0.02),
+                       ("decoder.blocks.3", 0.02), ("decoder.blocks.4", 0.02)):
+        t = eng.read_tensor(name, 2).float().cpu().permute(0, 3, 1, 2)
+        f = feats[name]
+        assert t.shape == f.shape, name
+        assert (t - f).abs().mean() <= frac * f.std(), (name, (t - f).abs().mean().item(), f.std().item())
+
+
+def test_config3_whole_batch_on_one_gpu_offsets_beyond_2g(cuda_device):
+    """All 64 images of config 3 on ONE GPU: the stem output alone is 64 x 512 x 512 x 64 bf16 = 2.1 GB, so pixel
+    offsets pass 2^31 bytes (and 2^30 elements); images computed in the big batch equal the same images alone."""
+    ref, m = make_pair("resnet34", cuda_device)
+    small = O.image_like_u8(4, 1024, seed=23)
+    u8 = small.repeat(16, 1, 1, 1)
+    u8[40:44] = torch.flip(small, dims=[2])               # not all images identical
+    u8 = u8.to(cuda_device)
+    mask, logits = m.predict_mask(u8, 0.5, return_logits=True)
+    l4 = m.predict_mask(u8[60:64].contiguous(), 0.5, return_logits=True)[1]
+    assert torch.equal(logits[60:64], l4)
+    assert torch.equal(logits[0:4], logits[60:64])        # identical inputs, first and last slots of the arena
+    assert not torch.equal(logits[40:44], logits[0:4])
+    assert torch.equal(mask, (logits[:, 0] > 0).to(torch.uint8) * 255)
+
+
+def test_full_size_config4_r50_768(cuda_device):
+    """BASELINE config 4: resnet50, 768x768, batch 32 (2.4 GB arena, K = 27 648 decoder conv)."""
+    ref, m = make_pair("resnet50", cuda_device)
+    u8 = O.image_like_u8(32, 768, seed=31).to(cuda_device)
+    logits = _size_properties(m, ref, u8, 17, cuda_device)
+    # batch 4 (another plan of the same engine) gives the same bits as the batch-32 run
+    assert torch.equal(m.predict_mask(u8[8:12].contiguous(), 0.5, return_logits=True)[1], logits[8:12])
+
+
+def test_large_decoder_resnet50_reference_yaml(cuda_device):
+    """reference src/configs/unet_watermark_large.yaml: resnet50, decoder (1024, 512, 256, 128, 64), 768 input
+    (run at 96x96 here: the channel plan, not the size, is what differs from the default)."""
+    dec = (1024, 512, 256, 128, 64)
+    ref, m = make_pair("resnet50", cuda_device, dec=dec)
+    x = O.image_like_input(1, 96, seed=8)
+    with torch.no_grad():
+        y32 = ref(x)
+    assert_close_to_oracle(m(x.to(cuda_device)).cpu(), y32, O.forward_bf16_emulated(ref, x))

@@ -7,6 +7,7 @@ UWM_DBG bit mask (bench-only; results are garbage when set): 1 skip activation l
 """
 import argparse
 import os
+os.environ.setdefault("UWM_TOOLS", "1")   # measurement build of the library (python -m unet_watermark_b200.build --tools)
 import sys
 
 import torch

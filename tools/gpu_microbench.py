@@ -1,5 +1,7 @@
 """tcgen05.mma rate on this GPU: cycles per group of 4 MMAs (M=128 x N x K=16 each) under different
 synchronisation patterns.  mode 0 raw; 1 +commit per group; 3 +wait(complete)+commit; 4 full handshake."""
+import os
+os.environ.setdefault("UWM_TOOLS", "1")   # measurement build of the library (python -m unet_watermark_b200.build --tools)
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,6 @@
 """Cycles per repetition of single synchronisation primitives (one warp, nothing else on the SM)."""
+import os
+os.environ.setdefault("UWM_TOOLS", "1")   # measurement build of the library (python -m unet_watermark_b200.build --tools)
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

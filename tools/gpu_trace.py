@@ -4,6 +4,7 @@
 """
 import argparse
 import os
+os.environ.setdefault("UWM_TOOLS", "1")   # measurement build of the library (python -m unet_watermark_b200.build --tools)
 import sys
 
 import torch

@@ -8,6 +8,7 @@ first/median/last CTA exit - i.e. how much of a launch's wall time lies outside 
 """
 import argparse
 import os
+os.environ.setdefault("UWM_TOOLS", "1")   # measurement build of the library (python -m unet_watermark_b200.build --tools)
 import sys
 
 import torch

@@ -2,6 +2,8 @@
 
     UWM_TRACE_KH=4 python tools/gpu_trace_model.py
 """
+import os
+os.environ.setdefault("UWM_TOOLS", "1")   # measurement build of the library (python -m unet_watermark_b200.build --tools)
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -12,7 +12,9 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("UWM_LIB_PATH") or os.path.join(_HERE, "lib", "libuwm_b200.so")   # override: A/B of two builds
+# UWM_LIB_PATH: A/B of two builds; UWM_TOOLS=1: the measurement build (python -m unet_watermark_b200.build --tools)
+LIB_PATH = os.environ.get("UWM_LIB_PATH") or os.path.join(
+    _HERE, "lib", "libuwm_b200_tools.so" if os.environ.get("UWM_TOOLS") == "1" else "libuwm_b200.so")
 
 IN_F32_NCHW = 0
 IN_U8_NHWC = 1
@@ -81,6 +83,10 @@ SIGNATURES = {
     "uwm_model_profile": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_float, C.c_char_p,
                                     C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.c_int, _P]),
+}
+
+# exported only by the tools build (-DUWM_BENCH_TOOLS); bound when present
+TOOLS_SIGNATURES = {
     "uwm_debug_set_trace": (C.c_int, [_P]),
     "uwm_debug_prim_cost": (C.c_int, [C.c_int, C.c_int, _P, _P]),
     "uwm_debug_handshake": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
@@ -104,6 +110,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in TOOLS_SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     _lib = lib
     return lib
 

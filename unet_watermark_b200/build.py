@@ -11,6 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libuwm_b200.so")
+OUT_TOOLS = os.path.join(HERE, "lib", "libuwm_b200_tools.so")   # -DUWM_BENCH_TOOLS: uwm_debug_* exports, UWM_DBG, in-kernel trace
 SOURCES = ["uwm_api.cu"]
 DEPS = ["uwm_api.cu", "conv_tc.cuh", "conv_halo.cuh", "glue.cuh", "ptx_sm100.cuh", "microbench.cuh", os.path.join("..", "..", "include", "uwm.h")]
 
@@ -22,19 +23,23 @@ NVCC_FLAGS = [
 ]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(OUT):
+def needs_build(out: str = OUT) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return OUT
+def build(force: bool = False, verbose: bool = False, tools: bool = False) -> str:
+    """tools=False: the product library.  tools=True: the measurement build (same kernels plus the sizing
+    micro-benchmarks, the UWM_DBG pipeline-isolation switches and the in-kernel trace) used by tools/gpu_*.py."""
+    out = OUT_TOOLS if tools else OUT
+    if not force and not needs_build(out):
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, *(["-DUWM_BENCH_TOOLS"] if tools else []), "-o", out,
+           *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -43,8 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tools="--tools" in sys.argv))

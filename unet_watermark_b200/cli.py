@@ -4,7 +4,7 @@ The reference documents ``main.py predict --input <dir|file> --output <dir> --mo
 (reference src/cli.py:352-354, README.md:106-108) but only registers ``train | repair | auto-train``
 (reference src/cli.py:371,398,468).  This module implements the documented ``predict`` command with the
 flags of the reference's ``repair`` step 1 (reference src/cli.py:400-409,424): ``--input --output --model
---config --device --limit`` plus ``--batch-size --threshold --no-sigmoid``.  ``train``, ``repair`` and
+--config --device --limit`` plus ``--batch-size --threshold --sigmoid``.  ``train``, ``repair`` and
 ``auto-train`` orchestrate external tools and are out of scope.
 
 Multi-GPU: launch under ``torchrun --nproc-per-node N``; each rank takes every N-th file of the
@@ -58,14 +58,18 @@ def predict_command(args):
 
     cfg = get_cfg_defaults()
     if args.config and os.path.exists(args.config):
-        update_config(cfg, args.config)
+        update_config(cfg, args.config, strict=False)      # every YAML the reference ships loads (unknown keys kept + logged)
     elif args.config:
         print(f"警告: 配置文件不存在: {args.config}，使用默认配置")
     cfg.defrost()
     cfg.MODEL.NAME = args.model_name or cfg.MODEL.NAME
-    if cfg.MODEL.NAME == "UnetPlusPlus" and not args.model_name:
-        # the reference default architecture (config.py:15) is outside this hot path; the path is 'Unet'
-        cfg.MODEL.NAME = "Unet"
+    if cfg.MODEL.NAME != "Unet":
+        # No silent remapping: 'UnetPlusPlus' is the reference's default (config.py:15) and what its YAMLs set, but
+        # such a checkpoint has a different decoder (nested dense blocks) and cannot be loaded into the Unet path.
+        print(f"错误: MODEL.NAME={cfg.MODEL.NAME!r} 不受支持: the B200 mask path implements 'Unet' "
+              f"(resnet34/resnet50). A {cfg.MODEL.NAME} checkpoint cannot be loaded into it. If the checkpoint "
+              f"was trained with MODEL.NAME: Unet, pass --model-name Unet (or set it in the YAML).")
+        return 2
     if args.encoder:
         cfg.MODEL.ENCODER_NAME = args.encoder
     if args.img_size:
@@ -76,7 +80,7 @@ def predict_command(args):
 
     os.makedirs(args.output, exist_ok=True)
     predictor = WatermarkPredictor(model_path=args.model, config=cfg, device=device, batch_size=args.batch_size,
-                                   sigmoid=not args.no_sigmoid, num_workers=args.workers)
+                                   sigmoid=args.sigmoid, num_workers=args.workers)
     t0 = time.time()
     tmp = None
     if os.path.isfile(args.input):           # single image: same code path over a one-file folder view
@@ -114,7 +118,10 @@ def build_parser():
     p.add_argument("--save-mask", action="store_true", help="(compat) masks are always saved")
     p.add_argument("--batch-size", type=int, default=16)
     p.add_argument("--threshold", type=float, default=None, help="二值化阈值 (默认: cfg.PREDICT.THRESHOLD)")
-    p.add_argument("--no-sigmoid", action="store_true", help="threshold the raw output (reference predict.py:624)")
+    p.add_argument("--sigmoid", action="store_true",
+                   help="threshold sigmoid(output) (watermark_filter.py:136-150 convention) instead of the reference "
+                        "predictor's raw output > threshold (predict.py:624-625, the default)")
+    p.add_argument("--no-sigmoid", action="store_true", help="(compat; the raw-output convention is the default)")
     p.add_argument("--model-name", type=str, default=None, help="override cfg.MODEL.NAME (default: Unet)")
     p.add_argument("--encoder", type=str, default=None, help="override cfg.MODEL.ENCODER_NAME")
     p.add_argument("--img-size", type=int, default=None, help="override cfg.DATA.IMG_SIZE")

@@ -13,11 +13,15 @@ checkpoints written by the reference trainer — which pickle the live CfgNode u
 from __future__ import annotations
 
 import copy
+import logging
 import sys
 import types
 from typing import Any
 
 import yaml
+
+
+logger = logging.getLogger(__name__)
 
 
 class CfgNode(dict):
@@ -73,10 +77,10 @@ class CfgNode(dict):
     def merge_from_other_cfg(self, other: "CfgNode"):
         _merge(other, self, [])
 
-    def merge_from_file(self, path: str):
+    def merge_from_file(self, path: str, allow_new: bool = False):
         with open(path, "r", encoding="utf-8") as f:
             loaded = yaml.safe_load(f) or {}
-        _merge(CfgNode(loaded), self, [])
+        _merge(CfgNode(loaded), self, [], allow_new)
 
     def merge_from_list(self, kv):
         if len(kv) % 2:
@@ -104,13 +108,19 @@ class CfgNode(dict):
         return yaml.safe_dump(self.to_dict(), **kwargs)
 
 
-def _merge(src: CfgNode, dst: CfgNode, path):
+def _merge(src: CfgNode, dst: CfgNode, path, allow_new: bool = False):
     for k, v in src.items():
         full = ".".join(path + [k])
         if k not in dst:
-            raise KeyError(f"Non-existent config key: {full}")      # yacs behaviour
+            if not allow_new:
+                raise KeyError(f"Non-existent config key: {full}")      # yacs behaviour
+            # reference YAMLs such as unet_text_watermark.yaml carry keys the reference's own schema does not
+            # declare (DATA.TEXT_ENHANCEMENT, TEXT_WATERMARK.*): the mask path never reads them
+            logger.warning("config key %s is not in the schema; kept as given", full)
+            dict.__setitem__(dst, k, CfgNode(v) if isinstance(v, dict) else copy.deepcopy(v))
+            continue
         if isinstance(v, dict) and isinstance(dst[k], CfgNode):
-            _merge(v if isinstance(v, CfgNode) else CfgNode(v), dst[k], path + [k])
+            _merge(v if isinstance(v, CfgNode) else CfgNode(v), dst[k], path + [k], allow_new)
         else:
             dict.__setitem__(dst, k, copy.deepcopy(v))
 
@@ -194,10 +204,12 @@ def get_cfg_defaults() -> CfgNode:
     return _C.clone()
 
 
-def update_config(cfg: CfgNode, config_file: str):
-    """Merge a YAML file and freeze (reference src/configs/config.py:92-96)."""
+def update_config(cfg: CfgNode, config_file: str, strict: bool = True):
+    """Merge a YAML file and freeze (reference src/configs/config.py:92-96).  ``strict=True`` is yacs' behaviour
+    (KeyError on keys outside the schema); the CLI passes ``strict=False`` so that every YAML shipped with the
+    reference loads (unknown keys are kept and logged)."""
     cfg.defrost()
-    cfg.merge_from_file(config_file)
+    cfg.merge_from_file(config_file, allow_new=not strict)
     cfg.freeze()
 
 

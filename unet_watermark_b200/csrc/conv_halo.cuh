@@ -154,14 +154,14 @@ __device__ __forceinline__ void umma_halo(uint32_t tmem_d, uint32_t a_lo, uint32
 // MMA 160+3*tile+{0 accumulator free, 1 first stage landed, 2 all MMAs issued}, epilogue 400+2*tile+{0 accumulator
 // full, 1 tile stored}
 __device__ __forceinline__ void halo_trace(const HaloKArgs& p, int slot) {
-  if (p.trace && blockIdx.x == 0 && slot < 600) p.trace[slot] = clock64();
+  if (UWM_TRACE_OF(p) && blockIdx.x == 0 && slot < 600) p.trace[slot] = clock64();
 }
 
 // dbg bit 8 (with a trace buffer of >= 1024 + 4*grid slots): every CTA stamps its start and exit in nanoseconds
 // and in SM cycles,
 // so consecutive launches show the gap between one grid's last exit and the next grid's first tile
 __device__ __forceinline__ void halo_trace_cta(const HaloKArgs& p, int which) {
-  if (p.trace && (p.dbg & 8)) {
+  if (UWM_TRACE_OF(p) && (UWM_DBG_OF(p) & 8)) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.trace[1024 + 4 * blockIdx.x + which] = (long long)t;
@@ -425,7 +425,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const uint32_t b_slice_units = p.b_slice_bytes >> 4;
     const uint32_t b_stage_units = b_stage_bytes >> 4;
     const uint32_t bn = (uint32_t)p.block_n;
-    const bool skip_mma = p.dbg & 2;
+    const bool skip_mma = UWM_DBG_OF(p) & 2;
     const uint32_t idesc_half = make_idesc_bf16(kTileM, SPX == 1 ? p.block_n >> 1 : p.block_n);
     const uint32_t idesc_quarter = make_idesc_bf16(kTileM, SPX == 1 ? p.block_n >> 2 : p.block_n);
     if (elect_one() && (!CG2 || crank == 0)) {
@@ -613,7 +613,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       // Residual convs with staged TMA stores: the residual box of the warp's first (sub-tile, 64 channels) unit is
       // TMA-loaded into the warp's staging buffer NOW, long before the accumulator is complete; the epilogue adds it
       // in place.  (Lane-per-pixel global loads exposed an L2 round trip per 16-column item in the drain.)
-      const bool res_tma = tma_out && (p.res != nullptr) && !(p.dbg & 4);
+      const bool res_tma = tma_out && (p.res != nullptr) && !(UWM_DBG_OF(p) & 4);
       if (res_tma && lane == 0 && c_first * 4 < min(p.block_n, p.cout - col0)) {
         bulk_wait_read<0>();                 // the previous tile's last store has read the buffer out
         mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
@@ -625,7 +625,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       tc_fence_after();
       if (warp == 2 && lane == 0) halo_trace(p, 400 + 2 * it);
 
-      if (p.dbg & 4) {
+      if (UWM_DBG_OF(p) & 4) {
         // bench-only: no epilogue work
       } else if (p.head) {
         if (S2D) {
@@ -827,14 +827,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             halo_trace(p, 16 + 2 * nstage);
             if (CG2) {       // both CTAs' boxes complete on the leader's barrier (CG2 kernels have one source)
               const uint32_t fa = lead(afull_bar(s));
-              if (!(p.dbg & 1)) {
+              if (!(UWM_DBG_OF(p) & 1)) {
                 if (crank == 0) mbar_arrive_expect_tx(afull_bar(s), 2u * (uint32_t)NPIX * ROWB);   // both CTAs' boxes
                 tma_load_4d_cg2(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, fa, ch * KC, wbase * p.a_scale,
                                 hbase * p.a_scale, t.img);
               } else if (crank == 0) {
                 mbar_arrive(afull_bar(s));
               }
-            } else if (!(p.dbg & 1)) {
+            } else if (!(UWM_DBG_OF(p) & 1)) {
               mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
               if (ch < p.split_chunk)
                 tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase * p.a_scale,
@@ -871,7 +871,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         __syncwarp();
         if (lt == 0) halo_trace(p, 16 + 2 * nstage);
         const uint32_t dst0 = a_base + (uint32_t)s * A_STAGE_BYTES;
-        if (p.mix && ch >= p.split_chunk && !(p.dbg & 1)) {
+        if (p.mix && ch >= p.split_chunk && !(UWM_DBG_OF(p) & 1)) {
           // the skip source is stored at the conv's resolution: one TMA box (swizzled layout) instead of a gather;
           // the barrier expects one arrival per loader thread, so thread 0's expect_tx arrival is one of them
           if (lt == 0) {
@@ -885,7 +885,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           if (++s == p.a_stages) { s = 0; ph ^= 1u; }
           continue;
         }
-        if (!(p.dbg & 1)) {
+        if (!(UWM_DBG_OF(p) & 1)) {
 #pragma unroll 4
           for (int i = lt; i < ITEMS; i += kHaloLoaderThreads) {
             const int c = i & (CPS - 1);

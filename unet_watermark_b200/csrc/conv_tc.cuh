@@ -22,6 +22,16 @@
 #pragma once
 #include "ptx_sm100.cuh"
 
+// Pipeline-isolation switches and the in-kernel trace exist only in the tools build (-DUWM_BENCH_TOOLS); in the product
+// library these fold to constants and the compiler drops the code behind them.
+#ifdef UWM_BENCH_TOOLS
+#define UWM_DBG_OF(p) ((p).dbg)
+#define UWM_TRACE_OF(p) ((p).trace)
+#else
+#define UWM_DBG_OF(p) 0
+#define UWM_TRACE_OF(p) (static_cast<long long*>(nullptr))
+#endif
+
 namespace uwm {
 
 constexpr int kConvThreads = 192;
@@ -145,7 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
       __syncwarp();
     }
     const uint32_t tx1 = kABytes + (p.b_resident ? 0u : b_bytes);
-    const bool skip_tma = (p.dbg == 1 || p.dbg == 7);
+    const bool skip_tma = (UWM_DBG_OF(p) == 1 || UWM_DBG_OF(p) == 7);
     const uint32_t b_off0 = (uint32_t)kpack * p.a_stage_bytes;
     const bool leader = elect_one();
     int s = 0; uint32_t ph = 0;
@@ -188,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
     const uint32_t bres_lo0 = ((bres_base & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t stage_units = ring_stage >> 4, a_units = p.a_stage_bytes >> 4, b_units = p.b_stage_bytes >> 4;
     const uint32_t b_off_units = (uint32_t)kpack * a_units;
-    const bool skip_mma = (p.dbg == 2 || p.dbg == 7);
+    const bool skip_mma = (UWM_DBG_OF(p) == 2 || UWM_DBG_OF(p) == 7);
     const bool leader = elect_one();
     if (p.b_resident && leader) mbar_wait(bres_bar, 0);
     int s = 0; uint32_t ph = 0;
@@ -250,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
 
-      if (p.dbg == 4 || p.dbg == 7) {
+      if (UWM_DBG_OF(p) == 4 || UWM_DBG_OF(p) == 7) {
         // bench-only: no epilogue work at all
       } else if (p.head) {
         uint32_t v[16];
@@ -298,7 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act,
             o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
             o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
             o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            if (p.dbg != 3) {
+            if (UWM_DBG_OF(p) != 3) {
               *reinterpret_cast<uint4*>(orow + c) = o0;
               *reinterpret_cast<uint4*>(orow + c + 8) = o1;
             } else if (o0.x == 0x12345678u && o1.w == 0x9abcdef0u) {   // bench-only: keep the math alive

@@ -24,7 +24,9 @@
 #include "conv_tc.cuh"
 #include "conv_halo.cuh"
 #include "glue.cuh"
-#include "microbench.cuh"
+#ifdef UWM_BENCH_TOOLS
+#include "microbench.cuh"   // sizing micro-benchmarks: only in the tools build (python -m unet_watermark_b200.build --tools)
+#endif
 
 using namespace uwm;
 
@@ -130,14 +132,22 @@ static void launch_pdl_pairs(void (*kernel)(KArgs...), unsigned grid, unsigned b
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// per-device caches (a process may drive several GPUs through separate engines)
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -212,7 +222,15 @@ static FastDiv make_fastdiv(int d) {
   return f;
 }
 
-static long long* g_halo_trace = nullptr;   // bench-only (uwm_debug_set_trace)
+// Pipeline-isolation switches (UWM_DBG) and the in-kernel trace corrupt results by design: they exist only in the tools
+// build (-DUWM_BENCH_TOOLS); the product library ignores the variable and never carries a trace pointer.
+#ifdef UWM_BENCH_TOOLS
+static long long* g_halo_trace = nullptr;   // uwm_debug_set_trace
+static int dbg_bits() { const char* e = getenv("UWM_DBG"); return e ? atoi(e) : 0; }
+#else
+static long long* const g_halo_trace = nullptr;
+static int dbg_bits() { return 0; }
+#endif
 
 static bool halo_enabled() {
   static int v = -1;
@@ -279,7 +297,7 @@ static int build_halo_spx(const ConvSpec& s, ConvLaunch* L) {
   a.relu = s.relu;
   a.shuffle = s.shuffle;
   a.ep_tma = 0; a.ep_cols = 16;
-  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.dbg = dbg_bits();
   a.trace = g_halo_trace;
   a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x); a.src[0].pitch = s.x_pitch; a.src[0].h = s.h; a.src[0].w = s.w;
   a.src[1].ptr = static_cast<const __nv_bfloat16*>(s.x2); a.src[1].pitch = s.x2_pitch; a.src[1].h = 2 * s.h; a.src[1].w = 2 * s.w;
@@ -393,7 +411,7 @@ static int build_halo_s2(const ConvSpec& s, ConvLaunch* L) {
   a.out_pitch = s.out_pitch;
   a.relu = s.relu;
   a.ep_tma = 1; a.ep_cols = 64;
-  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.dbg = dbg_bits();
   a.trace = g_halo_trace;
   a.src[0].ptr = static_cast<const __nv_bfloat16*>(s.x); a.src[0].pitch = s.x_pitch; a.src[0].h = s.h; a.src[0].w = s.w;
   a.src[1] = a.src[0];
@@ -634,11 +652,13 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.relu = s.relu;
   a.head = s.head; a.apply_sigmoid = s.apply_sigmoid;
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
-  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.dbg = dbg_bits();
   a.trace = g_halo_trace;
   { static const bool mix_on = []{ const char* e = getenv("UWM_MIX"); return !(e && e[0] == '0'); }();
     a.mix = (!a_tma && s.x2 && mix_on) ? 1 : 0; }
-  { const char* e = getenv("UWM_TRACE_KH"); if (e && atoi(e) != kh) a.trace = nullptr; }   // bench-only: trace one filter shape
+#ifdef UWM_BENCH_TOOLS
+  { const char* e = getenv("UWM_TRACE_KH"); if (e && atoi(e) != kh) a.trace = nullptr; }   // trace one filter shape
+#endif
   a.shuffle = (par_tiles && ep_tma) ? 0 : s.shuffle;      // the strided TMA view does the pixel shuffle
   a.ep_tma = ep_tma ? 1 : 0; a.ep_cols = ep_tma ? 64 : 16;
   { const char* e = getenv("UWM_VERBOSE");
@@ -811,7 +831,7 @@ static int build_conv_stream(const ConvSpec& s, ConvLaunch* L) {
   a.head = s.head; a.apply_sigmoid = s.apply_sigmoid;
   a.logits = s.logits; a.mask = s.mask; a.thr_logit = s.thr_logit;
 
-  { const char* e = getenv("UWM_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.dbg = dbg_bits();
   L->grid = grid;
   L->smem = fixed + (size_t)stages * ring_stage;
 
@@ -942,7 +962,9 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
 }
 
 static int set_conv_attrs() {
-  static bool done = false;
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: tracked per device, not per process
+  static bool done_dev[kMaxDevices] = {false};
+  bool& done = done_dev[current_device()];
   if (done) return UWM_OK;
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
@@ -1579,6 +1601,9 @@ extern "C" int uwm_model_set_layer(uwm_model* m, int i, const void* wgt, int64_t
   if (w_elems != L.d.w_elems || b_elems != L.d.b_elems)
     return fail(UWM_EINVAL, "set_layer(%s): expected %lld weight / %lld bias elements, got %lld / %lld", L.d.conv_key,
                 (long long)L.d.w_elems, (long long)L.d.b_elems, (long long)w_elems, (long long)b_elems);
+  // a forward may still be in flight on a non-blocking stream: the blocking copies below are only ordered against
+  // the legacy stream, so drain the device first (weight uploads are rare)
+  if (i == 0) CUDA_TRY(cudaDeviceSynchronize());
   if (!L.d_w) CUDA_TRY(cudaMalloc(&L.d_w, (size_t)w_elems * 2));
   if (!L.d_b) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&L.d_b), (size_t)b_elems * 4));
   CUDA_TRY(cudaMemcpy(L.d_w, wgt, (size_t)w_elems * 2, cudaMemcpyDefault));
@@ -1830,6 +1855,7 @@ extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int
   return n;
 }
 
+#ifdef UWM_BENCH_TOOLS
 // ------------------------------------------------------------------------------------------
 // micro-benchmarks (sizing experiments; not part of the product path)
 // ------------------------------------------------------------------------------------------
@@ -1854,3 +1880,4 @@ extern "C" int uwm_debug_handshake(int iters, int variant, int blocks, long long
   handshake_kernel<<<blocks, 64, 0, st>>>(iters, variant, d_cycles);
   return post_launch("handshake_kernel", st);
 }
+#endif  // UWM_BENCH_TOOLS

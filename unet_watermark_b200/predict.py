@@ -7,8 +7,8 @@ Mirrors the UNet step of ``WatermarkPredictor`` (reference src/predict.py): mode
 and the OpenCV mask post-processing (``_optimize_mask``) are out of scope.
 
 Mask conventions, selectable with ``sigmoid``:
-  * ``sigmoid=True``  (default): ``cv2.resize(sigmoid(out)) > thr``  — watermark_filter.py:136-150
-  * ``sigmoid=False``:           ``cv2.resize(out) > thr``           — predict.py:620-625
+  * ``sigmoid=False`` (default, the reference predictor): ``cv2.resize(out) > thr``   — predict.py:620-625
+  * ``sigmoid=True``:  ``cv2.resize(sigmoid(out)) > thr``                            — watermark_filter.py:136-150
 When the image already has the network size no resize happens and the uint8 mask comes straight
 from the fused head kernel.
 """
@@ -59,7 +59,7 @@ class WatermarkPredictor:
     """UNet mask predictor (step 1 of the reference's pipeline), batched."""
 
     def __init__(self, model_path, config_path=None, config=None, device="cuda", batch_size: Optional[int] = None,
-                 sigmoid: bool = True, num_workers: int = 8):
+                 sigmoid: bool = False, num_workers: int = 8):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("unet_watermark_b200 runs the mask path on CUDA (sm_100a) only; "
@@ -93,22 +93,38 @@ class WatermarkPredictor:
             raise
 
     # -- files -----------------------------------------------------------------------------------
-    def _get_image_files(self, input_folder, output_folder=None, limit=None):
-        """Same discovery rules as the reference (:114-160): 6 extensions x 2 cases, de-duplicated and
-        sorted, images whose ``<stem>_mask.png`` exists are skipped, optional random ``limit``."""
+    def _get_image_files(self, input_folder, output_folder=None, limit=None, rank: int = 0, world_size: int = 1,
+                         seed: int = 0):
+        """Same discovery rules as the reference (:114-160): 6 extensions x 2 cases, de-duplicated and sorted,
+        images whose ``<stem>_mask.png`` exists are skipped, optional random ``limit``.
+
+        Multi-rank order of operations (a stable partition needs it): the FULL sorted list is sharded first
+        (rank r owns files r, r+W, ...), the skip-existing filter then runs inside each shard - a rank that lists
+        the directory late, after other ranks have written masks, still owns exactly the same files - and
+        ``limit`` selects the same seeded random subset of the unfiltered list on every rank before sharding
+        (the reference shuffles unseeded in its single process, :155-157)."""
         files = []
         for ext in IMAGE_EXTENSIONS:
             files.extend(glob.glob(os.path.join(input_folder, ext)))
             files.extend(glob.glob(os.path.join(input_folder, ext.upper())))
         files = sorted(set(files))
-        if output_folder and os.path.exists(output_folder):
-            files = [p for p in files
-                     if not os.path.exists(os.path.join(output_folder,
-                                                        f"{os.path.splitext(os.path.basename(p))[0]}_mask.png"))]
         if limit is not None and limit > 0 and len(files) > limit:
-            random.shuffle(files)
-            files = files[:limit]
-        return files
+            if world_size > 1:
+                random.Random(seed).shuffle(files)
+                files = sorted(files[:limit])
+            else:                                          # single process: the reference's order (filter, then shuffle)
+                files = self._skip_existing(files, output_folder)
+                random.shuffle(files)
+                return files[:limit]
+        files = shard_for_rank(files, rank, world_size)
+        return self._skip_existing(files, output_folder)
+
+    @staticmethod
+    def _skip_existing(files, output_folder):
+        if not (output_folder and os.path.exists(output_folder)):
+            return files
+        return [p for p in files
+                if not os.path.exists(os.path.join(output_folder, f"{os.path.splitext(os.path.basename(p))[0]}_mask.png"))]
 
     # -- pre / post ------------------------------------------------------------------------------
     def _load_resized(self, path: str):
@@ -158,8 +174,7 @@ class WatermarkPredictor:
         returns ``[{image_path, mask_path, watermark_ratio}]`` for images with a non-empty mask."""
         import cv2
         os.makedirs(mask_output_folder, exist_ok=True)
-        files = self._get_image_files(input_folder, mask_output_folder, limit=limit)
-        files = shard_for_rank(files, rank, world_size)
+        files = self._get_image_files(input_folder, mask_output_folder, limit=limit, rank=rank, world_size=world_size)
         if not files:
             logger.warning("在 %s 中未找到未处理的图像文件", input_folder)
             return []

@@ -186,7 +186,9 @@ class Unet(nn.Module):
         self.name = f"u-{encoder_name}"
         self._initialize()
         self._engines: Dict[tuple, Engine] = {}
-        self._weights_token = None
+        self._weights_gen = 0          # bumped whenever parameters may have been replaced or edited
+        self._tensors_gen = -1
+        self._tensors: list = []
         self.use_cuda_graph = True
 
     # smp SegmentationModel.initialize(): decoder kaiming-uniform, head xavier-uniform
@@ -211,16 +213,21 @@ class Unet(nn.Module):
                                f"divisible by 32. Consider pad your images to shape ({nh}, {nw}).")
 
     def _token(self):
-        # cheap fingerprint of "weights changed": in-place updates bump _version, .to()/load replace storage
-        t = []
-        for p in (self.encoder.conv1.weight, self.encoder.bn1.running_var, self.segmentation_head[0].weight,
-                  self.decoder.blocks[0].conv1[0].weight, self.decoder.blocks[4].conv2[1].running_mean):
-            t.append((p.data_ptr(), p._version))
-        return tuple(t)
+        """Fingerprint of "weights changed": a generation counter bumped by load_state_dict / .to() / refresh_weights
+        plus the autograd version counter of EVERY parameter and buffer (in-place updates - optimizer steps,
+        ``p.add_()``, ``p.copy_()`` - bump it).  Writes through ``p.data`` bypass the version counter: call
+        ``refresh_weights()`` after those."""
+        if self._tensors_gen != self._weights_gen:
+            self._tensors = [t for t in list(self.parameters()) + list(self.buffers())]
+            self._tensors_gen = self._weights_gen
+        v = 0
+        for t in self._tensors:
+            v += t._version
+        return (self._weights_gen, v)
 
     def refresh_weights(self):
-        """Re-fold BatchNorm and re-upload packed weights (call after modifying parameters in place)."""
-        self._weights_token = None
+        """Re-fold BatchNorm and re-upload packed weights (needed after edits through ``.data``)."""
+        self._weights_gen += 1
 
     def _engine_for(self, b: int, h: int, w: int, device: torch.device) -> Engine:
         key = (h, w, device.index if device.index is not None else torch.cuda.current_device())
@@ -231,27 +238,27 @@ class Unet(nn.Module):
             eng = Engine(self.encoder_name, self.decoder_channels, h, w, max(b, 1), device)
             self._engines[key] = eng
         tok = self._token()
-        if not eng.weights_loaded or getattr(eng, "_token", None) != tok or self._weights_token != tok:
+        if not eng.weights_loaded or getattr(eng, "_token", None) != tok:      # compared per engine
             eng.load_weights(self.state_dict())
             eng._token = tok
-            self._weights_token = tok
         return eng
 
     def _apply(self, fn, *a, **k):
-        self._weights_token = None
+        self._weights_gen += 1
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, *a, **k):
         state_dict = {k_: v for k_, v in state_dict.items()
                       if not k_.startswith("encoder.fc.")}       # smp ResNetEncoder drops fc.*
-        self._weights_token = None
+        self._weights_gen += 1
         return super().load_state_dict(state_dict, *a, **k)
 
     def __getstate__(self):
         # engines hold C handles / device workspaces: never pickled or deep-copied
         d = self.__dict__.copy()
         d["_engines"] = {}
-        d["_weights_token"] = None
+        d["_tensors"] = []
+        d["_tensors_gen"] = -1
         return d
 
     # ------------------------------------------------------------------ forward
