@@ -241,6 +241,65 @@ int    uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int batch,
                          char* names, float* ms, double* flops, double* bytes, int n_max,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Image-side kernels of the reference's mask path: ragged batches of images of
+ * different sizes travel in one packed buffer described by a table of uwm_image_desc.  Every entry takes the
+ * table twice: h_desc (host copy, used for launch geometry and validation) and d_desc (device copy, read by the
+ * kernels).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct uwm_image_desc {
+  int64_t offset;     /* start of the image inside the packed buffer, in elements of that buffer */
+  int32_t width;      /* pixels */
+  int32_t height;
+  int32_t pitch;      /* elements between consecutive rows (>= width * channels) */
+  int32_t reserved;
+} uwm_image_desc;
+
+/* cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_LINEAR) on uint8 3-channel images, bit-exact with OpenCV's
+ * 11-bit fixed-point path (incl. its INTER_AREA shortcut for an exact 2x reduction) - the A.Resize of
+ * get_val_transform (reference src/utils/dataset.py:389-395, src/predict.py:598-602).
+ *   d_src  : packed uint8 HxWx3 images (descriptor i: offset, width, height, row pitch in bytes)
+ *   swap_rb: != 0 reads BGR (cv2.imread order) and writes RGB (reference src/predict.py:595 cvtColor folded in)
+ *   d_dst  : uint8 [n, dst_h, dst_w, 3] - the UWM_IN_U8_NHWC input of uwm_model_forward */
+int uwm_resize_bilinear_u8(const uint8_t* d_src, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n,
+                           int dst_w, int dst_h, int swap_rb, uint8_t* d_dst, void* stream);
+
+/* (cv2.resize(map, (W0, H0)) > threshold) * 255 per image (reference src/predict.py:620-625): bilinear resize of the
+ * network's float output to each image's original size with OpenCV's float operation order, then binarisation.
+ *   d_maps : fp32 [n, src_h, src_w] (logits, or probabilities for the sigmoid convention)
+ *   desc i : where mask i goes in d_masks (offset, width = W0, height = H0, row pitch in bytes)
+ *   d_masks: packed uint8 masks {0,255} (or NULL);  d_resized_f32: optional parity tap, same layout in floats */
+int uwm_mask_upscale_threshold(const float* d_maps, int n, int src_w, int src_h, const uwm_image_desc* h_desc,
+                               const uwm_image_desc* d_desc, float threshold, uint8_t* d_masks, float* d_resized_f32,
+                               void* stream);
+
+/* reference WatermarkPredictor._optimize_mask (src/predict.py:161-301) on a ragged batch of uint8 masks, in place:
+ * threshold 127, elliptical open / close / dilate sequence of the chosen strategy, 8-connected components and the
+ * area rules (largest component | area > 200 | > 50 | > 100).  Bit-exact with the OpenCV calls of the reference.
+ *   mode: 0 'watermark' (:232-273), 1 'text' (:192-230), 2 'mixed' (:275-301)
+ * d_workspace: uwm_mask_postprocess_workspace(h_desc, n) bytes of device scratch. */
+size_t uwm_mask_postprocess_workspace(const uwm_image_desc* h_desc, int n);
+int uwm_mask_postprocess(uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n, int mode,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* reference _analyze_text_features (src/predict.py:443-508): d_out[i] = {components scoring > 0.5, components} of
+ * mask i.  score_mask: bit (3*ia + ib)*3 + ic set when partial scores (aspect class ia, density class ib, area class
+ * ic; 0 = best class) sum to more than 0.5 in the reference's float arithmetic (tabulated by the host). */
+int uwm_mask_text_features(const uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n,
+                           unsigned score_mask, int32_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Single operations for the parity tests (same kernels as uwm_mask_postprocess).
+ * uwm_mask_morphology: cv2.erode / dilate / morphologyEx(OPEN | CLOSE) with cv2.getStructuringElement(shape, (w, h)),
+ *   default anchor and border, `iterations` times, in place.  op 0 erode, 1 dilate, 2 open, 3 close.
+ * uwm_mask_components: cv2.connectedComponentsWithStats(mask, connectivity=8) as per-pixel root index (-1 =
+ *   background) plus, AT each root pixel, area, OpenCV's label-order key and (optional) bbox {x0,y0,x1,y1}. */
+int uwm_mask_morphology(uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n, int op,
+                        int shape, int ksize_w, int ksize_h, int iterations, void* d_workspace, size_t workspace_bytes,
+                        void* stream);
+int uwm_mask_components(const uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n,
+                        int32_t* d_labels, int32_t* d_area, int32_t* d_order, int32_t* d_bbox, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ---- bench tools: exported only by the tools build of the library (-DUWM_BENCH_TOOLS; python -m
  * unet_watermark_b200.build --tools -> lib/libuwm_b200_tools.so).  The product library has none of these, nor the
  * UWM_DBG pipeline-isolation switches. ---- */

@@ -28,6 +28,12 @@ PACK_TAPS_SKIP_PART = 6
 PACK_UP2X_SHUFFLE_X_PART = 7
 
 
+class ImageDesc(C.Structure):
+    """uwm_image_desc: one image of a ragged batch inside a packed buffer."""
+    _fields_ = [("offset", C.c_int64), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class LayerDesc(C.Structure):
     _fields_ = [
         ("conv_key", C.c_char * 96),
@@ -83,6 +89,13 @@ SIGNATURES = {
     "uwm_model_profile": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_float, C.c_char_p,
                                     C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.c_int, _P]),
+    "uwm_resize_bilinear_u8": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "uwm_mask_upscale_threshold": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
+    "uwm_mask_postprocess_workspace": (C.c_size_t, [_P, C.c_int]),
+    "uwm_mask_postprocess": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "uwm_mask_text_features": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint, _P, _P, C.c_size_t, _P]),
+    "uwm_mask_morphology": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "uwm_mask_components": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
 }
 
 # exported only by the tools build (-DUWM_BENCH_TOOLS); bound when present

@@ -68,6 +68,9 @@ static int post_launch(const char* what, cudaStream_t st) {
 }
 
 extern "C" const char* uwm_last_error(void) { return g_err; }
+// shared with the library's other translation units (uwm_imgproc.cu); not part of the public header
+extern "C" void uwm_internal_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
+extern "C" void uwm_internal_count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 extern "C" int uwm_abi_version(void) { return 1; }
 extern "C" uint64_t uwm_kernel_launch_count(void) { return g_launches.load(); }
 

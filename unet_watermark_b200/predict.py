@@ -1,16 +1,26 @@
 """Mask-inference surface of the reference predictor, batched and B200-native.
 
-Mirrors the UNet step of ``WatermarkPredictor`` (reference src/predict.py): model load
-(:68-99), file discovery / skip-existing (:114-160), single-image ``predict_mask`` (:303-368) and
-``step1_batch_predict_watermark_masks`` (:560-664) — but runs the network through
-``libuwm_b200.so`` in batches instead of one image per forward.  The IOPaint / OCR steps 2-5
-and the OpenCV mask post-processing (``_optimize_mask``) are out of scope.
+Mirrors the UNet step of ``WatermarkPredictor`` (reference src/predict.py): model load (:68-99), file discovery /
+skip-existing (:114-160), single-image ``predict_mask`` (:303-368), ``step1_batch_predict_watermark_masks``
+(:560-664) with its watermark-type detection (:414-558) and mask post-processing (:161-301).  The IOPaint / OCR
+steps 2-5 of the repair pipeline are out of scope.
+
+Where the work runs (per batch of images of arbitrary sizes):
+
+    CPU threads   cv2.imread (BGR, original size) -> one pinned, packed staging buffer          reference :591-595
+    GPU           resize_u8 (cv2 INTER_LINEAR, bit-exact; BGR->RGB folded in)                   reference :598-602
+                  -> prep (Normalize) + Unet forward (tcgen05 kernels)                          reference :605-617
+                  -> bilinear upscale to each original size + threshold -> uint8 masks          reference :620-625
+                  -> [_analyze_text_features on the GPU; Canny/Sobel statistics on CPU threads] reference :414-558
+                  -> _optimize_mask (bit-packed morphology, 8-connected components, area rules)  reference :161-301
+    CPU threads   cv2.imwrite(<stem>_mask.png), watermark ratio                                 reference :629-639
 
 Mask conventions, selectable with ``sigmoid``:
   * ``sigmoid=False`` (default, the reference predictor): ``cv2.resize(out) > thr``   — predict.py:620-625
   * ``sigmoid=True``:  ``cv2.resize(sigmoid(out)) > thr``                            — watermark_filter.py:136-150
-When the image already has the network size no resize happens and the uint8 mask comes straight
-from the fused head kernel.
+Post-processing (``post_process=True`` = the reference's step 1): ``mask_type='auto'`` detects the watermark type per
+image like the reference; a fixed type ('watermark' | 'text' | 'mixed') skips the detection (as ``predict_mask``
+does, reference :303-368).
 """
 from __future__ import annotations
 
@@ -24,6 +34,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from . import imgproc
 from .config import get_cfg_defaults, install_yacs_shim, update_config
 from .unet_model import create_model_from_config
 
@@ -55,11 +66,77 @@ def load_checkpoint_state(model_path: str, map_location="cpu") -> Tuple[Dict[str
     return ckpt, {"epoch": "Unknown", "val_loss": "Unknown"}
 
 
+def analyze_ocr_features(image_rgb: np.ndarray, mask_binary: np.ndarray) -> float:
+    """Edge-density / gradient-direction score of the masked image (reference src/predict.py:510-558, same OpenCV
+    calls).  Canny + float64 Sobel statistics: host work, run on the decode threads."""
+    import cv2
+    try:
+        masked = cv2.bitwise_and(image_rgb, cv2.cvtColor(mask_binary, cv2.COLOR_GRAY2RGB))
+        gray = cv2.cvtColor(masked, cv2.COLOR_RGB2GRAY)
+        n_mask = np.sum(mask_binary > 0)
+        edge_density = np.sum(cv2.Canny(gray, 50, 150) > 0) / n_mask if n_mask > 0 else 0
+        angles = np.arctan2(cv2.Sobel(gray, cv2.CV_64F, 0, 1, ksize=3), cv2.Sobel(gray, cv2.CV_64F, 1, 0, ksize=3))
+        angle_variance = np.var(angles[mask_binary > 0]) if n_mask > 0 else 0
+        score = 0
+        if 0.1 <= edge_density <= 0.4:
+            score += 0.5
+        elif 0.05 <= edge_density < 0.1 or 0.4 < edge_density <= 0.6:
+            score += 0.2
+        if 1.0 <= angle_variance <= 3.0:
+            score += 0.5
+        elif 0.5 <= angle_variance < 1.0 or 3.0 < angle_variance <= 4.0:
+            score += 0.2
+        return min(score, 1.0)
+    except Exception as e:  # noqa: BLE001 - reference :556-558
+        logger.debug("OCR特征分析失败: %s", e)
+        return 0.0
+
+
+def watermark_type_from_scores(text_score: float, ocr_score: float) -> str:
+    """reference src/predict.py:430-438."""
+    total = text_score * 0.6 + ocr_score * 0.4
+    if total > 0.7:
+        return "text"
+    if total > 0.3:
+        return "mixed"
+    return "watermark"
+
+
+def enhance_text_features(image_rgb: np.ndarray) -> np.ndarray:
+    """reference src/predict.py:370-404 (CLAHE / Canny / sharpen pre-enhancement of the 'text' and 'mixed' single-image
+    modes), the same OpenCV calls on the host."""
+    import cv2
+    gray = cv2.cvtColor(image_rgb, cv2.COLOR_RGB2GRAY)
+    enhanced_gray = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(gray)
+    edges = cv2.dilate(cv2.Canny(enhanced_gray, 50, 150), cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2)), iterations=1)
+    out = image_rgb.copy()
+    edge_mask = edges > 0
+    for i in range(3):
+        ch = out[:, :, i].astype(np.float32)
+        ch[edge_mask] = np.clip(ch[edge_mask] * 1.2, 0, 255)
+        out[:, :, i] = ch.astype(np.uint8)
+    return cv2.filter2D(out, -1, np.array([[-1, -1, -1], [-1, 9, -1], [-1, -1, -1]]))
+
+
+class _Staging:
+    """Pinned host staging buffers that grow on demand (two of each: batch i+1 is filled while batch i is in flight)."""
+
+    def __init__(self):
+        self.bufs: Dict[Tuple[str, int], torch.Tensor] = {}
+
+    def get(self, kind: str, slot: int, nbytes: int) -> torch.Tensor:
+        b = self.bufs.get((kind, slot))
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+            self.bufs[(kind, slot)] = b
+        return b
+
+
 class WatermarkPredictor:
-    """UNet mask predictor (step 1 of the reference's pipeline), batched."""
+    """UNet mask predictor (step 1 of the reference's pipeline), batched, pre/post-processing on the GPU."""
 
     def __init__(self, model_path, config_path=None, config=None, device="cuda", batch_size: Optional[int] = None,
-                 sigmoid: bool = False, num_workers: int = 8):
+                 sigmoid: bool = False, num_workers: int = 8, post_process: Optional[bool] = None, mask_type: str = "auto"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("unet_watermark_b200 runs the mask path on CUDA (sm_100a) only; "
@@ -70,10 +147,15 @@ class WatermarkPredictor:
             self.cfg = get_cfg_defaults()
             if config_path and os.path.exists(config_path):
                 update_config(self.cfg, config_path)
+        if mask_type not in ("auto", "watermark", "text", "mixed"):
+            raise ValueError(f"mask_type {mask_type!r}: expected auto | watermark | text | mixed")
         self.sigmoid = sigmoid
+        self.mask_type = mask_type
+        self.post_process = bool(getattr(self.cfg.PREDICT, "POST_PROCESS", True)) if post_process is None else bool(post_process)
         self.img_size = int(self.cfg.DATA.IMG_SIZE)
         self.batch_size = int(batch_size or getattr(self.cfg.PREDICT, "BATCH_SIZE", 8))
         self.num_workers = num_workers
+        self._staging = _Staging()
         self.model, self.model_info = self._load_unet_model(model_path)
         logger.info("mask predictor ready on %s (batch %d, %dx%d)", self.device, self.batch_size, self.img_size,
                     self.img_size)
@@ -126,47 +208,91 @@ class WatermarkPredictor:
         return [p for p in files
                 if not os.path.exists(os.path.join(output_folder, f"{os.path.splitext(os.path.basename(p))[0]}_mask.png"))]
 
-    # -- pre / post ------------------------------------------------------------------------------
-    def _load_resized(self, path: str):
-        """cv2.imread -> RGB -> bilinear resize to the network size (the Resize of get_val_transform,
-        reference src/utils/dataset.py:389-395); Normalize is fused into the GPU prep kernel."""
+    # -- decode (CPU threads) ----------------------------------------------------------------------
+    @staticmethod
+    def _decode(path: str):
+        """cv2.imread: BGR uint8 at the original size (reference :591); None if unreadable."""
         import cv2
-        img = cv2.imread(path)
-        if img is None:
-            return None
-        h0, w0 = img.shape[:2]
-        rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
-        if (h0, w0) != (self.img_size, self.img_size):
-            rgb = cv2.resize(rgb, (self.img_size, self.img_size), interpolation=cv2.INTER_LINEAR)
-        return np.ascontiguousarray(rgb), (w0, h0)
+        return cv2.imread(path)
 
-    def _masks_for_batch(self, batch_u8: torch.Tensor, sizes: List[Tuple[int, int]], threshold: float):
-        """uint8 NHWC host batch -> list of uint8 {0,255} masks at the original sizes."""
-        import cv2
+    # -- one batch on the GPU ----------------------------------------------------------------------
+    def _masks_for_images(self, images_bgr: List[np.ndarray], threshold: float, slot: int = 0,
+                          mask_types: Optional[List[str]] = None, pool: Optional[ThreadPoolExecutor] = None
+                          ) -> Tuple[List[np.ndarray], List[str]]:
+        """BGR uint8 images of arbitrary sizes -> (uint8 {0,255} masks at the original sizes, mask types used)."""
+        n = len(images_bgr)
         s = self.img_size
-        x = batch_u8.to(self.device, non_blocking=True)
-        need_float = any(sz != (s, s) for sz in sizes)
-        if not need_float:
-            m = self.model.predict_mask(x, threshold, sigmoid=self.sigmoid).cpu().numpy()
-            return [m[i] for i in range(len(sizes))]
-        out = (self.model.predict_proba(x) if self.sigmoid else self.model(x))[:, 0].cpu().numpy()
-        masks = []
-        for i, (w0, h0) in enumerate(sizes):
-            mi = out[i] if (w0, h0) == (s, s) else cv2.resize(out[i], (w0, h0))
-            masks.append((mi > threshold).astype(np.uint8) * 255)
-        return masks
+        dev = self.device
+        sizes = [(im.shape[1], im.shape[0]) for im in images_bgr]
+        # 1. pack into pinned staging, one H2D copy
+        src = imgproc.RaggedBatch(sizes, channels=3)
+        stage = self._staging.get("in", slot, src.total)
+        host_np = stage.numpy()
+
+        def put(i):
+            d = src.host[i]
+            host_np[d.offset:d.offset + d.pitch * d.height].reshape(d.height, d.pitch)[:] = images_bgr[i].reshape(d.height, -1)
+        if pool is not None and n > 1:
+            list(pool.map(put, range(n)))
+        else:
+            for i in range(n):
+                put(i)
+        with torch.cuda.device(dev):
+            packed = stage[:src.total].to(dev, non_blocking=True)
+            src.to(dev, stream_non_blocking=True)
+            # 2. resize to the network size (bit-exact cv2 INTER_LINEAR; BGR -> RGB in the read), forward
+            x = imgproc.resize_bilinear_u8(packed, src, s, s, swap_rb=True)
+            maps = self.model.predict_proba(x) if self.sigmoid else self.model(x)           # fp32 [n,1,S,S]
+            # 3. bilinear upscale to every original size + threshold -> packed uint8 masks
+            dst = imgproc.RaggedBatch(sizes, channels=1, device=dev)
+            masks = imgproc.mask_upscale_threshold(maps, dst, threshold)
+            types = list(mask_types) if mask_types is not None else [self.mask_type] * n
+            if self.post_process:
+                ws = None
+                if any(t == "auto" for t in types):
+                    # reference _detect_watermark_type: geometric score on the GPU, Canny/Sobel statistics on CPU threads
+                    text_scores = imgproc.mask_text_features(masks, dst)
+                    raw = masks.cpu()
+                    def ocr(i):
+                        import cv2
+                        return analyze_ocr_features(cv2.cvtColor(images_bgr[i], cv2.COLOR_BGR2RGB), dst.view(raw, i).numpy())
+                    idx = [i for i, t in enumerate(types) if t == "auto"]
+                    ocr_scores = list(pool.map(ocr, idx)) if pool is not None else [ocr(i) for i in idx]
+                    for i, o in zip(idx, ocr_scores):
+                        types[i] = watermark_type_from_scores(text_scores[i], o)
+                # 4. _optimize_mask per type (one ragged launch sequence per type present in the batch)
+                for t in sorted(set(types)):
+                    sel = [i for i, ti in enumerate(types) if ti == t]
+                    if len(sel) == n:
+                        imgproc.mask_postprocess(masks, dst, t)
+                    else:
+                        sub = imgproc.RaggedBatch([sizes[i] for i in sel], channels=1, device=dev,
+                                                  pitches=[dst.host[i].pitch for i in sel],
+                                                  offsets=[dst.host[i].offset for i in sel])
+                        imgproc.mask_postprocess(masks, sub, t)
+            out_stage = self._staging.get("out", slot, dst.total)
+            out_stage[:dst.total].copy_(masks, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        out_np = out_stage.numpy()
+        result = []
+        for i in range(n):
+            d = dst.host[i]
+            result.append(out_np[d.offset:d.offset + d.pitch * d.height].reshape(d.height, d.pitch)[:, :d.width].copy())
+        return result, types
 
     # -- public API ------------------------------------------------------------------------------
     def predict_mask(self, image_path, mask_type="watermark"):
-        """Single image -> uint8 {0,255} mask at the original resolution (reference :303-368, without the
-        OpenCV post-processing / text-enhancement branches, which are out of scope)."""
-        item = self._load_resized(image_path)
-        if item is None:
+        """Single image -> uint8 {0,255} mask at the original resolution (reference :303-368): forward, bilinear
+        resize to the original size, threshold, ``_optimize_mask(mask, mask_type)``."""
+        import cv2
+        image = self._decode(image_path)
+        if image is None:
             raise ValueError(f"无法读取图像: {image_path}")
-        rgb, size = item
+        if mask_type in ("text", "mixed"):                      # reference :323-325 (host-side pre-enhancement)
+            image = cv2.cvtColor(enhance_text_features(cv2.cvtColor(image, cv2.COLOR_BGR2RGB)), cv2.COLOR_RGB2BGR)
         thr = float(getattr(self.cfg.PREDICT, "THRESHOLD", 0.5))
-        batch = torch.from_numpy(rgb).unsqueeze(0)
-        return self._masks_for_batch(batch, [size], thr)[0]
+        masks, _ = self._masks_for_images([image], thr, mask_types=[mask_type])
+        return masks[0]
 
     def step1_batch_predict_watermark_masks(self, input_folder, mask_output_folder, limit=None, rank: int = 0,
                                             world_size: int = 1):
@@ -179,38 +305,44 @@ class WatermarkPredictor:
             logger.warning("在 %s 中未找到未处理的图像文件", input_folder)
             return []
         thr = float(getattr(self.cfg.PREDICT, "THRESHOLD", 0.5))
-        s, bs = self.img_size, self.batch_size
-        processed = []
-        pinned = [torch.empty(bs, s, s, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        bs = self.batch_size
+        processed: List[dict] = []
+
+        def write(path, mask):
+            base = os.path.splitext(os.path.basename(path))[0]
+            mask_path = os.path.join(mask_output_folder, f"{base}_mask.png")
+            cv2.imwrite(mask_path, mask)
+            wm = int(np.count_nonzero(mask))
+            if wm == 0:                                        # reference :642-645: all-black mask, not reported
+                return None
+            return {"image_path": path, "mask_path": mask_path,
+                    "watermark_ratio": wm / float(mask.shape[0] * mask.shape[1])}
+
         with ThreadPoolExecutor(max_workers=self.num_workers) as pool:
             chunks = [files[i:i + bs] for i in range(0, len(files), bs)]
-            pending = pool.map(self._load_resized, chunks[0]) if chunks else None
+            pending = [pool.submit(self._decode, p) for p in chunks[0]]
+            writes = []
             for ci, chunk in enumerate(chunks):
-                items = list(pending)
-                if ci + 1 < len(chunks):                      # decode the next batch while the GPU works
-                    pending = pool.map(self._load_resized, chunks[ci + 1])
-                paths, sizes, buf = [], [], pinned[ci & 1]
-                for path, item in zip(chunk, items):
-                    if item is None:
+                images = [f.result() for f in pending]
+                if ci + 1 < len(chunks):                      # decode the next batch while the GPU works on this one
+                    pending = [pool.submit(self._decode, p) for p in chunks[ci + 1]]
+                paths, imgs = [], []
+                for path, im in zip(chunk, images):
+                    if im is None:
                         logger.error("无法加载图像: %s", path)
                         continue
-                    buf[len(paths)].copy_(torch.from_numpy(item[0]))
                     paths.append(path)
-                    sizes.append(item[1])
+                    imgs.append(im)
                 if not paths:
                     continue
                 try:
-                    masks = self._masks_for_batch(buf[:len(paths)], sizes, thr)
+                    masks, _ = self._masks_for_images(imgs, thr, slot=ci & 1, pool=pool)
                 except Exception as e:  # noqa: BLE001 - per-batch failures are logged and skipped (:655-657)
                     logger.error("处理图像失败 %s: %s", paths, e)
                     continue
-                for path, mask in zip(paths, masks):
-                    base = os.path.splitext(os.path.basename(path))[0]
-                    mask_path = os.path.join(mask_output_folder, f"{base}_mask.png")
-                    cv2.imwrite(mask_path, mask)
-                    wm = int(np.count_nonzero(mask))
-                    if wm == 0:
-                        continue
-                    processed.append({"image_path": path, "mask_path": mask_path,
-                                      "watermark_ratio": wm / float(mask.shape[0] * mask.shape[1])})
+                writes.extend(pool.submit(write, p, m) for p, m in zip(paths, masks))      # PNG encode off the main thread
+            for f in writes:
+                r = f.result()
+                if r is not None:
+                    processed.append(r)
         return processed
