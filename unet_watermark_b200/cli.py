@@ -4,7 +4,7 @@ The reference documents ``main.py predict --input <dir|file> --output <dir> --mo
 (reference src/cli.py:352-354, README.md:106-108) but only registers ``train | repair | auto-train``
 (reference src/cli.py:371,398,468).  This module implements the documented ``predict`` command with the
 flags of the reference's ``repair`` step 1 (reference src/cli.py:400-409,424): ``--input --output --model
---config --device --limit`` plus ``--batch-size --threshold --sigmoid``.  ``train``, ``repair`` and
+--config --device --limit`` plus ``--batch-size --threshold --sigmoid --no-post-process --mask-type``.  ``train``, ``repair`` and
 ``auto-train`` orchestrate external tools and are out of scope.
 
 Multi-GPU: launch under ``torchrun --nproc-per-node N``; each rank takes every N-th file of the
@@ -80,7 +80,8 @@ def predict_command(args):
 
     os.makedirs(args.output, exist_ok=True)
     predictor = WatermarkPredictor(model_path=args.model, config=cfg, device=device, batch_size=args.batch_size,
-                                   sigmoid=args.sigmoid, num_workers=args.workers)
+                                   sigmoid=args.sigmoid, num_workers=args.workers,
+                                   post_process=False if args.no_post_process else None, mask_type=args.mask_type)
     t0 = time.time()
     tmp = None
     if os.path.isfile(args.input):           # single image: same code path over a one-file folder view
@@ -122,6 +123,11 @@ def build_parser():
                    help="threshold sigmoid(output) (watermark_filter.py:136-150 convention) instead of the reference "
                         "predictor's raw output > threshold (predict.py:624-625, the default)")
     p.add_argument("--no-sigmoid", action="store_true", help="(compat; the raw-output convention is the default)")
+    p.add_argument("--no-post-process", action="store_true",
+                   help="write the thresholded masks without the reference's _optimize_mask step (predict.py:161-301)")
+    p.add_argument("--mask-type", choices=["auto", "watermark", "text", "mixed"], default="auto",
+                   help="auto: detect the watermark type per image like the reference's step 1 (predict.py:414-441); "
+                        "a fixed type skips the detection (as predict_mask does)")
     p.add_argument("--model-name", type=str, default=None, help="override cfg.MODEL.NAME (default: Unet)")
     p.add_argument("--encoder", type=str, default=None, help="override cfg.MODEL.ENCODER_NAME")
     p.add_argument("--img-size", type=int, default=None, help="override cfg.DATA.IMG_SIZE")
