@@ -50,8 +50,8 @@ def predict_command(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev_str = args.device
-    if dev_str in ("auto", "cuda") and torch.cuda.is_available() and world > 1:
-        dev_str = f"cuda:{local_rank}"
+    if dev_str in ("auto", "cuda") and torch.cuda.is_available():
+        dev_str = f"cuda:{local_rank if world > 1 else torch.cuda.current_device()}"      # always an indexed device
     device = setup_device(dev_str)
     if device.type == "cuda":
         torch.cuda.set_device(device)

@@ -79,6 +79,7 @@ struct HaloKArgs {
   int n_img, h, w;
   int tiles_w, tiles_h, n_tiles, total_tiles;
   FastDiv div_ntiles, div_tw, div_th;
+  FastDiv div_total;                        // CHAIN: work item / total_tiles = layer
   // K loop: chunks of kc channels (one A stage each), all taps per chunk
   int chunks;
   int split_chunk;                          // chunks [0,split) come from src[0], the rest from src[1]
@@ -112,6 +113,57 @@ struct HaloKArgs {
   long long* trace;                         // bench-only: CTA 0 writes clock64() stamps of its pipeline events (tools/gpu_trace.py)
   int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
 };
+
+// ---- multi-layer chains (CHAIN): one persistent launch runs several same-shaped conv layers back to back ----------
+// The N = 128 streamed 3x3 layers of a ResNet stage have 128-256 tiles each on 148 SMs and spend a third of a
+// launch in fill, drain and the gap to the next launch.  A chain walks the work items (layer, tile) of up to
+// kMaxChainLayers consecutive layers of identical geometry in one grid: item i = layer * total_tiles + tile, CTA c
+// takes items c, c + G, ...  Layer l + 1 of image n may start as soon as every tile of image n of layer l has been
+// stored: the epilogue warps count their completed TMA stores into dep[l][n] (release), the activation loader
+// polls it (acquire) before it requests the halo of a tile of that image.  Accumulator double-buffering, the weight
+// ring and the activation ring run across layer boundaries, so only the first fill and the last drain are exposed
+// and the tiles of consecutive layers fill every SM.  Tensors touched inside a chain never alias each other
+// (build_plan extends their lifetimes over the chain), and a residual (layer l - 2's output of the same image) is
+// complete by transitivity.
+constexpr int kMaxChainLayers = 16;
+struct alignas(64) HaloLayerRef {
+  CUtensorMap tm_wgt, tm_out, tm_res, tm_a0;
+  const float* bias;
+  int relu, has_res;
+  int pad_[12];
+};
+struct HaloChain {
+  HaloLayerRef layer[kMaxChainLayers];
+  int n_layers;
+  int dep_target;                           // arrivals per (layer, image): tiles of one image x 8 epilogue warps
+  int* dep;                                 // [n_layers][n_img] counters, then one CTA ticket (all zero between launches)
+};
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all bulk-group operations of this thread have COMPLETED (writes performed), not only read their source
+template <int N>
+__device__ __forceinline__ void bulk_wait_done() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// orders generic-proxy accesses (the counters) against async-proxy accesses (TMA loads / stores) of this thread
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __noinline__ void chain_wait_dep(const int* ctr, int target) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(40);
+    if ((++spins & 4095u) != 0) continue;
+    if (t0 == 0) { t0 = clock64(); continue; }
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a dependency that can never complete is a protocol bug, not a wait
+      printf("uwm: chain dependency watchdog (block %d, counter %d < %d)\n", (int)blockIdx.x, ld_acquire_gpu(ctr), target);
+      __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -217,11 +269,13 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
 // blocks with 4x16 outputs in which plane (ph,pw) only meets taps {1-ph,2-ph} x {1-pw,2-pw}: the MMA loop issues those
 // 16 of the 36 (tap, k) pairs (N = 64 or 16 instead of 16 per MMA, 2.25x fewer MMAs per output pixel) and rows of
 // 128 bytes go in and out by TMA.  The head variant writes the 4 logits / mask bytes of a block to its 2x2 pixels.
-template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, int SPX = 0, bool S2D = false, bool CG2 = false>
+template <int KC, int KH, int KW, int TG, bool RESIDENT, bool A_TMA, int SPX = 0, bool S2D = false, bool CG2 = false,
+          bool CHAIN = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_constant__ CUtensorMap tm_out,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-                 const __grid_constant__ HaloKArgs p) {
+                 const __grid_constant__ HaloKArgs p, const HaloChain* __restrict__ chain) {
+  static_assert(!CHAIN || (SPX == 0 && !S2D && !CG2 && !RESIDENT && A_TMA), "chains: plain streamed TMA-fed convs only");
   constexpr int NT = KH * KW;
   constexpr bool SPXP = (SPX == 1 || SPX == 2);            // chunk / slice sequencing of the parity-plane forms
   constexpr int CPS = KC / 8;                               // 8-channel planes per stage
@@ -306,9 +360,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   const int G = gridDim.x;
   // tile sequence of this CTA: tiles blockIdx.x, +G, ... ; a CTA pair walks pair-tiles (two M tiles of one N tile)
   const int t_first = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int t_end = CG2 ? (p.total_tiles >> 1) : p.total_tiles;
+  const int n_layers = CHAIN ? chain->n_layers : 1;
+  const int t_end = CHAIN ? n_layers * p.total_tiles : (CG2 ? (p.total_tiles >> 1) : p.total_tiles);
   const int t_step = CG2 ? (G >> 1) : G;
+  // CHAIN: work item tl = layer * total_tiles + tile
+  auto layer_of = [&](int tl) { return CHAIN ? fast_div(tl, p.div_total) : 0; };
   auto tile_of = [&](int tl) {
+    if (CHAIN) return tl - fast_div(tl, p.div_total) * p.total_tiles;
     if (!CG2) return tl;
     const int mu = fast_div(tl, p.div_ntiles);
     return (2 * mu + (int)crank) * p.n_tiles + (tl - mu * p.n_tiles);
@@ -383,6 +441,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           }
           continue;
         }
+        const CUtensorMap* wmap = CHAIN ? &chain->layer[layer_of(tl)].tm_wgt : &tm_wgt;
         for (int ch = 0; ch < p.chunks; ++ch) {
           for (int tap0 = 0; tap0 < NT; tap0 += p.kpb) {
             if (leader) {
@@ -399,7 +458,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               } else {
                 mbar_arrive_expect_tx(bfull_bar(s), (uint32_t)p.kpb * slice_tx);
                 for (int j = 0; j < p.kpb; ++j)
-                  tma_load_2d(dst + (uint32_t)j * p.b_slice_bytes, &tm_wgt, bfull_bar(s),
+                  tma_load_2d(dst + (uint32_t)j * p.b_slice_bytes, wmap, bfull_bar(s),
                               (tap0 + j) * p.cin_total + ch * KC, ncol);
               }
             }
