@@ -130,7 +130,8 @@ struct alignas(64) HaloLayerRef {
   CUtensorMap tm_wgt, tm_out, tm_res, tm_a0;
   const float* bias;
   int relu, has_res;
-  int pad_[12];
+  int res_layer;                            // chain layer whose output is this layer's residual, -1: produced before the chain
+  int pad_[11];
 };
 struct HaloChain {
   HaloLayerRef layer[kMaxChainLayers];
@@ -493,7 +494,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       int sb = 0; uint32_t phb = 0;
       int it = 0;
       for (int tl = t_first; tl < t_end; tl += t_step, ++it) {
-      const int tile = tile_of(tl);
+      const int tile = (SPX == 3) ? tile_of(tl) : 0;
         const int acc = it & nacc_mask;
         const uint32_t tmem_acc = tmem_base + (uint32_t)acc * (TG * bn);
         mbar_wait_fast(acce_bar(acc), ((uint32_t)(it >> nacc_log2) & 1u) ^ 1u);
@@ -634,7 +635,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const int row = q * 32 + lane;           // accumulator row == pixel of the 8x16 sub-tile
     const int wi = row & (kHaloTW - 1);
     const int hi = row >> 3;
-    const float lo_clamp = p.relu ? 0.f : -INFINITY;
+    float lo_clamp = p.relu ? 0.f : -INFINITY;
     const uint32_t bn = (uint32_t)p.block_n;
     const int eset = (warp >= kHaloLoaderWarp0) ? 1 : 0;       // which of the two warps of this lane quarter
     constexpr int GN = (TG >= 2) ? TG / 2 : 1;                 // sub-tiles per warp: g = GSTEP*gi + g_first
@@ -643,8 +644,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const int c_first = (TG >= 2) ? 0 : 16 * eset, c_step = (TG >= 2) ? 16 : 32;
     const bool tma_out = p.ep_tma != 0;
     const int ewarp = (warp & 3) + 4 * eset;                                  // 0..7
-    // stage the bias (all 8 epilogue warps, then a named barrier among them)
-    for (int i = ewarp * 32 + lane; i < p.n_tiles * p.block_n; i += 256) s_bias[i] = __ldg(p.bias + i);
+    // stage the bias (all 8 epilogue warps, then a named barrier among them); a chain stages every layer's
+    const int cout_all = p.n_tiles * p.block_n;
+    if (CHAIN) {
+      for (int l = 0; l < n_layers; ++l) {
+        const float* bl = chain->layer[l].bias;
+        for (int i = ewarp * 32 + lane; i < cout_all; i += 256) s_bias[l * cout_all + i] = __ldg(bl + i);
+      }
+    } else {
+      for (int i = ewarp * 32 + lane; i < cout_all; i += 256) s_bias[i] = __ldg(p.bias + i);
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const uint32_t stg = stg_base + (uint32_t)ewarp * (32u * 128u);           // one 32-row x 128-byte buffer per warp
     // 128B swizzle of the 16-byte chunks of this lane's row: chunk index ^ (row & 7)
@@ -655,6 +664,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     int it = 0;
     for (int tl = t_first; tl < t_end; tl += t_step, ++it) {
       const int tile = tile_of(tl);
+      const int layer = layer_of(tl);
+      // per-layer epilogue parameters of a chain: output / residual maps, bias row, ReLU, residual flag
+      const CUtensorMap* omap = CHAIN ? &chain->layer[layer].tm_out : &tm_out;
+      const CUtensorMap* rmap = CHAIN ? &chain->layer[layer].tm_res : &tm_res;
+      const bool has_res = CHAIN ? (chain->layer[layer].has_res != 0) : (p.res != nullptr);
+      if (CHAIN) lo_clamp = chain->layer[layer].relu ? 0.f : -INFINITY;
       const int acc = it & nacc_mask;
       const HaloTile t = halo_decode<TG>(p, tile);
       const int oh = t.h0 + hi;
@@ -672,11 +687,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       // Residual convs with staged TMA stores: the residual box of the warp's first (sub-tile, 64 channels) unit is
       // TMA-loaded into the warp's staging buffer NOW, long before the accumulator is complete; the epilogue adds it
       // in place.  (Lane-per-pixel global loads exposed an L2 round trip per 16-column item in the drain.)
-      const bool res_tma = tma_out && (p.res != nullptr) && !(UWM_DBG_OF(p) & 4);
+      const bool res_tma = tma_out && has_res && !(UWM_DBG_OF(p) & 4);
+      if (CHAIN && res_tma && lane == 0) {
+        // the residual is an earlier chain layer's output of the same image: it must be complete before the first
+        // residual box of this tile is requested (the loader's own wait does not order THIS thread's TMA reads)
+        const int rl = chain->layer[layer].res_layer;
+        if (rl >= 0) { chain_wait_dep(chain->dep + rl * p.n_img + t.img, chain->dep_target); fence_proxy_async_all(); }
+      }
       if (res_tma && lane == 0 && c_first * 4 < min(p.block_n, p.cout - col0)) {
         bulk_wait_read<0>();                 // the previous tile's last store has read the buffer out
         mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
-        tma_load_4d(stg, &tm_res, resbar(ewarp), ec0 + c_first * 4, ex(t.w0 + g_first * kHaloTW), ey(t.h0 + q * 4), t.img);
+        tma_load_4d(stg, rmap, resbar(ewarp), ec0 + c_first * 4, ex(t.w0 + g_first * kHaloTW), ey(t.h0 + q * 4), t.img);
       }
 
       if (lane == 0) mbar_wait(accf_bar(acc), (uint32_t)(it >> nacc_log2) & 1u);
@@ -740,7 +761,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         // compile-time flags): a warp runs ~4-10 cycles per instruction here, so the per-item branches of a
         // run-time-configured loop cost as much as the arithmetic.
         const int ncols = min(p.block_n, p.cout - col0);
-        const uint32_t bsm = smem_u32(s_bias + col0);                     // folded-BN bias, staged in smem
+        const uint32_t bsm = smem_u32(s_bias + (CHAIN ? layer * cout_all : 0) + col0);   // folded-BN bias, staged in smem
         auto run_items = [&](auto tma_c, auto res_c, auto shuf_c) {
           constexpr bool TMA = decltype(tma_c)::value, RES = decltype(res_c)::value, SHUF = decltype(shuf_c)::value;
           constexpr int LOG2_JN = TMA ? 2 : 0, JN = 1 << LOG2_JN;           // chunks per column group
@@ -824,7 +845,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                      tma_store_4d(&tm_out, stg, ec0 + cg0, ex(t.w0 + g * kHaloTW), ey(t.h0 + q * 4), t.img);
+                      tma_store_4d(omap, stg, ec0 + cg0, ex(t.w0 + g * kHaloTW), ey(t.h0 + q * 4), t.img);
                       bulk_commit();
                       if (RES) {           // next unit of this tile: its residual box, once the store has read the buffer
                         const int gi_n = (n >> LOG2_JN) + 1;
@@ -833,7 +854,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                         if (cg_n < ncols) {
                           bulk_wait_read<0>();
                           mbar_arrive_expect_tx(resbar(ewarp), 32u * 128u);
-                          tma_load_4d(stg, &tm_res, resbar(ewarp), ec0 + cg_n, ex(t.w0 + g_n * kHaloTW), ey(t.h0 + q * 4), t.img);
+                          tma_load_4d(stg, rmap, resbar(ewarp), ec0 + cg_n, ex(t.w0 + g_n * kHaloTW), ey(t.h0 + q * 4), t.img);
                         }
                       }
                     }
@@ -854,16 +875,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
           }
         };
         using T_ = std::true_type; using F_ = std::false_type;
-        if (tma_out) { if (p.res) run_items(T_{}, T_{}, F_{}); else run_items(T_{}, F_{}, F_{}); }
+        if (tma_out) { if (has_res) run_items(T_{}, T_{}, F_{}); else run_items(T_{}, F_{}, F_{}); }
+        else if (CHAIN) { }                                       // chains always store through TMA
         else if (p.shuffle) { if (p.res) run_items(F_{}, T_{}, T_{}); else run_items(F_{}, F_{}, T_{}); }
         else if (p.res) run_items(F_{}, T_{}, F_{});
         else run_items(F_{}, F_{}, F_{});
       }
+
       // every tcgen05.ld of this accumulator set has completed (tcgen05.wait::ld above): hand the set back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (CG2 && crank != 0) mbar_arrive_cluster(lead(acce_bar(acc))); else mbar_arrive(acce_bar(acc)); }
       if (warp == 2 && lane == 0) halo_trace(p, 401 + 2 * it);
+      if (CHAIN && lane == 0) {
+        // (after the accumulator set went back to the MMA warp) this warp's stores of the tile are complete -> count
+        // them into the image's counter of this layer.  The stores went through the async proxy: wait for their
+        // completion (not just for the smem read), then a proxy fence, then the release.
+        bulk_wait_done<0>();
+        fence_proxy_async_all();
+        red_release_gpu_add(chain->dep + layer * p.n_img + t.img, 1);
+      }
     }
     if (tma_out && lane == 0) bulk_wait_read<0>();     // smem must outlive the last store's read
   } else {
@@ -881,6 +912,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         const int tile = tile_of(tl);
           const HaloTile t = halo_decode<TG>(p, tile);
           const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
+          const int layer = layer_of(tl);
+          const CUtensorMap* amap = CHAIN ? &chain->layer[layer].tm_a0 : &tm_a0;
+          if (CHAIN && layer > 0) {
+            // every tile of this image of the previous layer has been stored (acquire), then order the TMA reads after it
+            halo_trace(p, 500 + 2 * (nstage / p.chunks));            // trace: dependency wait of this item (begin / end)
+            chain_wait_dep(chain->dep + (layer - 1) * p.n_img + t.img, chain->dep_target);
+            fence_proxy_async_all();
+            halo_trace(p, 501 + 2 * (nstage / p.chunks));
+          }
           for (int ch = 0; ch < p.chunks; ++ch) {
             mbar_wait(aempty_bar(s), ph ^ 1u);
             halo_trace(p, 16 + 2 * nstage);
@@ -896,7 +936,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             } else if (!(UWM_DBG_OF(p) & 1)) {
               mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
               if (ch < p.split_chunk)
-                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a0, afull_bar(s), ch * KC, wbase * p.a_scale,
+                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, amap, afull_bar(s), ch * KC, wbase * p.a_scale,
                             hbase * p.a_scale, t.img);
               else if (SPXP) {
                 // parity plane (ph,pw) of the full-resolution skip source: halo block b is pixel 2b + parity
@@ -967,6 +1007,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CHAIN && threadIdx.x == 0) {
+    // the last CTA to finish (nobody polls any more) zeroes the counters for the next launch of this chain
+    int* ticket = chain->dep + n_layers * p.n_img;
+    __threadfence();
+    if (atomicAdd(ticket, 1) == G - 1) {
+      for (int i = 0; i < n_layers * p.n_img; ++i) chain->dep[i] = 0;
+      *ticket = 0;
+      __threadfence();
+    }
+  }
   if (CG2) cluster_sync_all();       // the peer may still signal this CTA's barriers / the leader still reads its smem
   if (warp == 1) { if (CG2) tmem_dealloc_cg2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols); }
   if (threadIdx.x == 0) halo_trace_cta(p, 1);

@@ -602,6 +602,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   a.div_ntiles = make_fastdiv(a.n_tiles);
   a.div_tw = make_fastdiv(a.tiles_w);
   a.div_th = make_fastdiv(a.tiles_h);
+  a.div_total = make_fastdiv(a.total_tiles);
   // CTA pairs (cta_group::2) for the streamed 3x3 kernels fed by TMA from one source: two M tiles of one N tile share
   // every weight slice, each CTA loading half of its rows
   // Measured (r34 512x512 B=16): it pays where a tile's streamed bytes outrun the fabric's ~43 B/clk per SM - layer4
@@ -873,6 +874,26 @@ static int build_conv_stream(const ConvSpec& s, ConvLaunch* L) {
 
 // Instantiation table of conv_halo_kernel<KC, KH, KW, TG, RESIDENT>.  L == nullptr: raise the dynamic
 // shared-memory limit of every instantiation (once); otherwise launch the one matching L.
+static const HaloChain* const kNoChain = nullptr;
+
+// Multi-layer chain kernels (conv_halo.cuh CHAIN): streamed 3x3, 64-channel chunks, TMA-fed.  L == nullptr: raise the
+// shared-memory limit (a chain stages every layer's bias on top of the single-layer budget).
+static int chain_dispatch(const ConvLaunch* L, const HaloChain* d_chain, cudaStream_t st) {
+#define UWM_HALO_CHAIN(TG)                                                                                        \
+  if (!L) {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<64, 3, 3, TG, false, true, 0, false, false, true>,             \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));                      \
+  } else if (L->tg == TG) {                                                                                       \
+    launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, 0, false, false, true>, L->grid, kHaloThreads, L->smem, \
+               st, L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs, d_chain);                       \
+    return UWM_OK;                                                                                                \
+  }
+  UWM_HALO_CHAIN(1) UWM_HALO_CHAIN(2)
+#undef UWM_HALO_CHAIN
+  if (!L) return UWM_OK;
+  return fail(UWM_ESTATE, "chain conv: no kernel instantiated for tg=%d", L->tg);
+}
+
 static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
 #define UWM_HALO_CASE1(KC, KH, KW, TG, RES, AT)                                                                 \
   if (!L) {                                                                                                     \
@@ -881,7 +902,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
   } else if (!L->spx && !L->s2d && !L->cg2 && L->kc == KC && L->kh == KH && L->kw == KW && L->tg == TG && (L->resident != 0) == RES && \
              (L->a_tma != 0) == AT) {                                                                           \
     launch_pdl(conv_halo_kernel<KC, KH, KW, TG, RES, AT>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt, L->tm_out, \
-               L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                                                   \
+               L->tm_res, L->tm_a0, L->tm_a1, L->hargs, kNoChain);                                                         \
     return UWM_OK;                                                                                              \
   }
 #define UWM_HALO_CASE(KC, KH, KW, TG, RES) UWM_HALO_CASE1(KC, KH, KW, TG, RES, false) UWM_HALO_CASE1(KC, KH, KW, TG, RES, true)
@@ -904,7 +925,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
   } else if (L->cg2 && L->tg == TG) {                                                                             \
     launch_pdl_pairs(conv_halo_kernel<64, 3, 3, TG, false, true, 0, false, true>, L->grid, kHaloThreads, L->smem, \
-                     st, L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                          \
+                     st, L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs, kNoChain);                \
     return UWM_OK;                                                                                                \
   }
   UWM_HALO_CG2(1) UWM_HALO_CG2(2)
@@ -917,7 +938,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
   } else if (L->s2d && L->tg == TG && L->kc == 64 && L->resident && L->a_tma) {                                   \
     launch_pdl(conv_halo_kernel<64, 3, 3, TG, true, true, 0, true>, L->grid, kHaloThreads, L->smem, st,           \
-               L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                    \
+               L->tm_wgt, L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs, kNoChain);                          \
     return UWM_OK;                                                                                                \
   }
   UWM_HALO_S2D(1) UWM_HALO_S2D(2) UWM_HALO_S2D(4)
@@ -930,7 +951,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
   } else if (L->spx == 1 && L->tg == TG) {                                                                             \
     launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, 1>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,     \
-               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
+               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs, kNoChain);                                     \
     return UWM_OK;                                                                                                \
   }
   UWM_HALO_SPX(1) UWM_HALO_SPX(2)
@@ -942,7 +963,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
   } else if (L->spx == 3 && L->tg == TG && !L->resident) {                                                        \
     launch_pdl(conv_halo_kernel<64, 3, 3, TG, false, true, 3>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,     \
-               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
+               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs, kNoChain);                                     \
     return UWM_OK;                                                                                                \
   }
   UWM_HALO_PAR(1) UWM_HALO_PAR(2)
@@ -954,7 +975,7 @@ static int halo_dispatch(const ConvLaunch* L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                      \
   } else if (L->spx == 2 && L->tg == TG) {                                                                        \
     launch_pdl(conv_halo_kernel<64, 2, 2, TG, false, true, 2>, L->grid, kHaloThreads, L->smem, st, L->tm_wgt,     \
-               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs);                                               \
+               L->tm_out, L->tm_res, L->tm_a0, L->tm_a1, L->hargs, kNoChain);                                     \
     return UWM_OK;                                                                                                \
   }
   UWM_HALO_S2(1) UWM_HALO_S2(2)
@@ -973,6 +994,7 @@ static int set_conv_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
   { int rc = halo_dispatch(nullptr, nullptr); if (rc) return rc; }
+  { int rc = chain_dispatch(nullptr, nullptr, nullptr); if (rc) return rc; }
   done = true;
   return UWM_OK;
 }
@@ -1239,6 +1261,7 @@ struct Op {
   bool side = false;          // independent of its neighbour in op order (downsample conv): forked graph branch
   bool join = false;          // first consumer of a side-branch result
   int layer = -1;
+  int chain_group = 0;        // > 0: consecutive convs of identical shape that may run as one multi-layer launch (conv_halo.cuh CHAIN)
   double flops_per_img = 0, bytes_per_img = 0;
 };
 struct Layer {
@@ -1253,11 +1276,16 @@ struct Layer {
 };
 struct Launch {          // one kernel of an instantiated plan
   OpType type;
-  ConvLaunch conv;       // OP_CONV / OP_HEAD
+  ConvLaunch conv;       // OP_CONV / OP_HEAD (a chain: its first layer, grid / smem / div_total of the whole chain)
   const void* src = nullptr; void* dst = nullptr;
   int n = 0, h = 0, w = 0, c = 0;
   long long src_pitch = 0, dst_pitch = 0;
   bool side = false, join = false;
+  int chain_group = 0;
+  int chain_len = 0;                       // > 1: multi-layer chain launch
+  HaloChain* d_chain = nullptr;            // device copy of the chain table (owned by the plan)
+  std::string name;
+  double flops_per_img = 0, bytes_per_img = 0;
 };
 struct GraphKey {        // caller-owned arguments baked into a captured forward
   const void* in; const void* logits; const void* mask; int in_fmt, apply_sigmoid; uint32_t thr_bits;
@@ -1269,6 +1297,7 @@ struct GraphKey {        // caller-owned arguments baked into a captured forward
 struct Plan {            // launches of one forward at a fixed batch size (+ the captured graphs)
   std::vector<Launch> launches;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::vector<void*> dev_allocs;           // chain tables and dependency counters
 };
 
 }  // namespace
@@ -1285,6 +1314,7 @@ struct uwm_model {
   uint8_t* arena = nullptr;
   double flops_per_img = 0;
   std::map<int, Plan> plans;
+  int last_plan_launches = 0;              // kernels per forward of the most recently used plan
   cudaStream_t cap_stream = nullptr, side_stream = nullptr;   // capture streams (main + forked branch)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
@@ -1404,6 +1434,35 @@ static int build_plan(uwm_model* m) {
   const int cs[5] = {enc_ch[3], enc_ch[2], enc_ch[1], enc_ch[0], 0};
   TRef skip[5];   // encoder feature feeding decoder block i (filled in as the encoder is laid out)
 
+  // decoder conv1 forms (see the decoder loop below), decided up front: the skip half of a two-launch conv1 is emitted
+  // right behind the encoder stage that produces its input, so it can join that stage's chain
+  static const bool spx_on = []{ const char* e = getenv("UWM_SPX"); return !(e && e[0] == '0'); }();
+  static const bool split_on = []{ const char* e = getenv("UWM_SPLIT_UPCAT"); return !(e && e[0] == '0'); }();
+  // Multi-layer chain launches are OPT-IN (UWM_CHAIN=1).  Measured r02 (B200, B = 16, 512x512): bit-identical results; the
+  // layer2 chain (8 convs, 256 tiles each) 137 us as one launch against 8 x ~17 us under programmatic dependent launch,
+  // the layer3 chain (12 convs, 128 tiles each on 148 SMs: every item depends on the round just before it) 244 us
+  // against 12 x ~17.5 us - the just-in-time per-image dependencies cost what fill / drain / launch gaps cost the
+  // single launches, so the step does not get faster (1.049 vs 1.054 ms with the layer2 chain only, 1.085 ms with both).
+  static const bool chain_on = []{ const char* e = getenv("UWM_CHAIN"); return e && e[0] == '1'; }();
+  bool spx_f[5], split_f[5];
+  TRef part_t[5];
+  for (int i = 0; i < 5; ++i) {
+    spx_f[i] = cs[i] > 0 && spx_on && subpixel_enabled() && 4 * dec[i] <= 256 && dec[i] % 16 == 0 && cx[i] % 64 == 0 && cs[i] % 64 == 0;
+    split_f[i] = cs[i] > 0 && !spx_f[i] && split_on && subpixel_enabled() && (dec[i] == 128 || dec[i] == 256) &&
+                 cx[i] % 64 == 0 && cs[i] % 64 == 0;
+  }
+  // Chain groups (conv_halo.cuh CHAIN): maximal runs of consecutive stride-1 3x3 convs with cin == cout >= 128 (streamed
+  // weights) at one resolution.  Whether a run really launches as one kernel is decided per batch size in
+  // instantiate(); here the runs are marked and their tensors' lifetimes extended over the run (no aliasing inside).
+  int next_group = 0, cur_group = 0, grp_c = 0, grp_h = 0;
+  auto chain_mark = [&](int cin, int cout, int k, int stride, int h) {
+    const bool ok = chain_on && halo_enabled() && k == 3 && stride == 1 && cin == cout && cin >= 128 && cin % 64 == 0;
+    if (ok && cur_group && grp_c == cin && grp_h == h) { m->ops.back().chain_group = cur_group; return; }
+    cur_group = ok ? ++next_group : 0; grp_c = cin; grp_h = h;
+    m->ops.back().chain_group = cur_group;
+  };
+  auto chain_break = [&]() { cur_group = 0; };
+
   // ---- input prep + stem ----
   TRef xs = m->dense(H / 2, W / 2, 16);
   { Op op; op.type = OP_PREP; op.name = "prep"; op.out = xs;
@@ -1442,9 +1501,11 @@ static int build_plan(uwm_model* m) {
         TRef t1 = m->dense(oh, ow, planes[li]);
         int l1 = add_layer(m, pre + ".conv1", pre + ".bn1", cur_c, planes[li], 3, stride, 1, 1, 0);
         add_conv(m, l1, x, t1, nullptr);
+        chain_mark(cur_c, planes[li], 3, stride, oh);
         int l2 = add_layer(m, pre + ".conv2", pre + ".bn2", planes[li], planes[li], 3, 1, 1, 1, 1);
         add_conv(m, l2, t1, out, &identity);
         m->ops.back().join = need_ds;
+        chain_mark(planes[li], planes[li], 3, 1, oh);
       } else {  // torchvision Bottleneck v1.5: stride on the 3x3
         TRef t1 = m->dense(cur_h, cur_w, planes[li]);
         int l1 = add_layer(m, pre + ".conv1", pre + ".bn1", cur_c, planes[li], 1, 1, 0, 1, 0);
@@ -1459,6 +1520,17 @@ static int build_plan(uwm_model* m) {
       x = out; cur_c = out_c; cur_h = oh; cur_w = ow;
     }
     m->named[fmt("encoder.layer%d", li + 1)] = x;
+    // skip half of the two-launch decoder conv1 that consumes this stage (stage li feeds decoder block 2 - li)
+    const int bi = 2 - li;
+    if (li < 3 && bi >= 0 && split_f[bi]) {
+      const std::string dpre = fmt("decoder.blocks.%d", bi);
+      part_t[bi] = m->dense(cur_h, cur_w, dec[bi]);
+      int la = add_layer(m, dpre + ".conv1.0", dpre + ".conv1.1", cs[bi], dec[bi], 3, 1, 1, /*relu=*/0, 0);
+      m->layers[la].d.pack = UWM_PACK_TAPS_SKIP_PART; m->layers[la].d.cin_skip = cs[bi];
+      add_conv(m, la, x, part_t[bi], nullptr);
+      if (!r50) chain_mark(cs[bi], dec[bi], 3, 1, cur_h);
+    }
+    chain_break();
   }
 
   // ---- decoder ----
@@ -1476,22 +1548,15 @@ static int build_plan(uwm_model* m) {
     t1.s2d = s2d;
     // sub-pixel forms (N = 4*cout <= 256 on the source grid): without a skip, and with a skip when both sources
     // split into 64-channel chunks (build_halo_spx)
-    static const bool spx_on = []{ const char* e = getenv("UWM_SPX"); return !(e && e[0] == '0'); }();
-    const bool spx = cs[i] > 0 && spx_on && subpixel_enabled() && 4 * dec[i] <= 256 && dec[i] % 16 == 0 &&
-                     cx[i] % 64 == 0 && cs[i] % 64 == 0;
+    const bool spx = spx_f[i];
     const bool subpixel = ((cs[i] == 0) && subpixel_enabled() && 4 * dec[i] <= 256) || spx;
     // Blocks whose sub-pixel form would need more than 256 GEMM columns (default decoder: blocks 0 and 1) run conv1 as
     // two launches: the skip half as an ordinary 3x3 conv into a partial-sum tensor (bias folded here, no ReLU), then
     // the upsampled half as a sub-pixel conv with one N tile per output parity (4 of 9 taps each) whose pixel-shuffle
     // epilogue adds that partial sum and applies the ReLU.  The partial sum is stored in bf16 (one extra rounding).
-    static const bool split_on = []{ const char* e = getenv("UWM_SPLIT_UPCAT"); return !(e && e[0] == '0'); }();
-    const bool split = cs[i] > 0 && !spx && split_on && subpixel_enabled() && (dec[i] == 128 || dec[i] == 256) &&
-                       cx[i] % 64 == 0 && cs[i] % 64 == 0;
+    const bool split = split_f[i];
     if (split) {
-      TRef part = m->dense(bh, bw, dec[i]);
-      int la = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cs[i], dec[i], 3, 1, 1, /*relu=*/0, 0);
-      m->layers[la].d.pack = UWM_PACK_TAPS_SKIP_PART; m->layers[la].d.cin_skip = cs[i];
-      add_conv(m, la, skip[i], part, nullptr);
+      TRef part = part_t[i];                     // the skip half ran right behind the encoder stage (see above)
       int lb = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i], dec[i], 3, 1, 1, /*relu=*/1, /*has_res=*/1, false,
                          /*shuffle=*/true);
       m->layers[lb].d.pack = UWM_PACK_UP2X_SHUFFLE_X_PART; m->layers[lb].d.cin_skip = cs[i];
@@ -1520,6 +1585,29 @@ static int build_plan(uwm_model* m) {
     if (op.out.buf >= 0) m->touch(op.out, i);
     if (op.has_res) m->touch(op.res, i);
     if (op.has_in2) m->touch(op.in2, i);
+  }
+  // tensors touched inside a chain group live for the whole group: layer l + 1 of one image runs while layer l of
+  // another is still in flight, so nothing inside the group may share memory
+  {
+    std::map<int, std::pair<int, int>> span;      // group -> [first op, last op]
+    for (int i = 0; i < (int)m->ops.size(); ++i) {
+      const int g = m->ops[i].chain_group;
+      if (!g) continue;
+      auto it = span.find(g);
+      if (it == span.end()) span[g] = {i, i}; else it->second.second = i;
+    }
+    for (int i = 0; i < (int)m->ops.size(); ++i) {
+      const Op& op = m->ops[i];
+      if (!op.chain_group) continue;
+      const auto sp = span[op.chain_group];
+      auto widen = [&](const TRef& t) {
+        if (t.buf < 0) return;
+        Buf& b = m->bufs[t.buf];
+        b.first = std::min(b.first, sp.first); b.last = std::max(b.last, sp.second);
+      };
+      widen(op.in); widen(op.out);
+      if (op.has_res) widen(op.res);
+    }
   }
   std::vector<int> order;
   for (int i = 0; i < (int)m->bufs.size(); ++i) if (m->bufs[i].last >= 0) order.push_back(i);
@@ -1581,7 +1669,10 @@ extern "C" int uwm_model_create(int encoder, const int* decoder_channels, int h,
 
 extern "C" int uwm_model_destroy(uwm_model* m) {
   if (!m) return UWM_OK;
-  for (auto& kv : m->plans) for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
+  for (auto& kv : m->plans) {
+    for (auto& g : kv.second.graphs) cudaGraphExecDestroy(g.second);
+    for (void* q : kv.second.dev_allocs) cudaFree(q);
+  }
   for (auto& L : m->layers) { if (L.d_w) cudaFree(L.d_w); if (L.d_b) cudaFree(L.d_b); }
   if (m->arena) cudaFree(m->arena);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
@@ -1615,18 +1706,26 @@ extern "C" int uwm_model_set_layer(uwm_model* m, int i, const void* wgt, int64_t
   return UWM_OK;
 }
 extern "C" size_t uwm_model_workspace_bytes(const uwm_model* m) { return m ? m->arena_bytes : 0; }
-extern "C" int uwm_model_num_kernels(const uwm_model* m) { return m ? (int)m->ops.size() : 0; }
+// kernels per forward: of the plan used last (chains merge several convs into one launch), else one per planned op
+extern "C" int uwm_model_num_kernels(const uwm_model* m) {
+  if (!m) return 0;
+  return m->last_plan_launches > 0 ? m->last_plan_launches : (int)m->ops.size();
+}
 extern "C" double uwm_model_flops_per_image(const uwm_model* m) { return m ? m->flops_per_img : 0.0; }
 
 // Instantiate the launches of one forward for `batch` images.
+static int merge_chains(std::vector<Launch>* ls, std::vector<void*>* dev_allocs);
+
 static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, float* d_logits, int apply_sigmoid,
-                       uint8_t* d_mask, float thr_logit, std::vector<Launch>* out) {
+                       uint8_t* d_mask, float thr_logit, std::vector<Launch>* out, std::vector<void*>* dev_allocs) {
   out->clear();
   out->reserve(m->ops.size());
   for (const Op& op : m->ops) {
     Launch L;
     L.type = op.type;
     L.side = op.side; L.join = op.join;
+    L.chain_group = op.chain_group;
+    L.name = op.name; L.flops_per_img = op.flops_per_img; L.bytes_per_img = op.bytes_per_img;
     switch (op.type) {
       case OP_PREP:
         L.src = d_in; L.dst = m->ptr(op.out); L.n = batch; L.h = m->H; L.w = m->W; L.c = in_fmt;
@@ -1681,6 +1780,89 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
     }
     out->push_back(L);
   }
+  return merge_chains(out, dev_allocs);
+}
+
+// Consecutive launches of one chain group that came out as the same kernel instantiation with the same geometry
+// become ONE multi-layer launch (conv_halo.cuh CHAIN).
+static int merge_chains(std::vector<Launch>* ls, std::vector<void*>* dev_allocs) {
+  static const int min_tiles = []{ const char* e = getenv("UWM_CHAIN_MIN_TILES"); return e ? atoi(e) : 0; }();
+  auto chainable = [](const Launch& L) {
+    const ConvLaunch& c = L.conv;
+    return L.type == OP_CONV && L.chain_group > 0 && c.hargs.total_tiles >= min_tiles && c.halo && !c.spx && !c.s2d && !c.cg2 && !c.resident && c.a_tma &&
+           c.kc == 64 && c.kh == 3 && c.kw == 3 && (c.tg == 1 || c.tg == 2) && c.hargs.ep_tma && !c.hargs.shuffle &&
+           c.hargs.split_chunk == c.hargs.chunks && c.hargs.a_scale == 1;
+  };
+  auto same_shape = [](const ConvLaunch& a, const ConvLaunch& b) {
+    const HaloKArgs &x = a.hargs, &y = b.hargs;
+    return a.tg == b.tg && x.n_img == y.n_img && x.h == y.h && x.w == y.w && x.chunks == y.chunks && x.block_n == y.block_n &&
+           x.n_tiles == y.n_tiles && x.cout == y.cout && x.kpb == y.kpb && x.a_stages == y.a_stages && x.b_stages == y.b_stages &&
+           x.total_tiles == y.total_tiles && x.tmem_cols == y.tmem_cols && x.nacc_log2 == y.nacc_log2 && x.cin_total == y.cin_total &&
+           x.b_slice_bytes == y.b_slice_bytes && a.smem == b.smem;
+  };
+  std::vector<Launch> out;
+  size_t i = 0;
+  while (i < ls->size()) {
+    size_t j = i + 1;
+    if (chainable((*ls)[i]))
+      while (j < ls->size() && j - i < (size_t)kMaxChainLayers && (*ls)[j].chain_group == (*ls)[i].chain_group &&
+             chainable((*ls)[j]) && same_shape((*ls)[i].conv, (*ls)[j].conv)) ++j;
+    const int n = (int)(j - i);
+    const size_t smem = (*ls)[i].conv.smem + (size_t)(n - 1) * (*ls)[i].conv.hargs.cout * 4;   // every layer's bias is staged
+    if (n < 2 || smem > 225u * 1024u) {
+      for (size_t k = i; k < j; ++k) out.push_back((*ls)[k]);
+      i = j;
+      continue;
+    }
+    HaloChain hc;
+    memset(&hc, 0, sizeof(hc));
+    Launch M = (*ls)[i];
+    M.name = "chain[" + std::to_string(n) + "] " + (*ls)[i].name + " .. " + (*ls)[j - 1].name;
+    M.flops_per_img = 0; M.bytes_per_img = 0;
+    for (int l = 0; l < n; ++l) {
+      const Launch& Lk = (*ls)[i + l];
+      HaloLayerRef& r = hc.layer[l];
+      r.tm_wgt = Lk.conv.tm_wgt; r.tm_out = Lk.conv.tm_out; r.tm_res = Lk.conv.tm_res; r.tm_a0 = Lk.conv.tm_a0;
+      r.bias = Lk.conv.hargs.bias; r.relu = Lk.conv.hargs.relu; r.has_res = Lk.conv.hargs.res != nullptr;
+      r.res_layer = -1;                      // which chain layer wrote this layer's residual (the epilogue waits for it)
+      for (int k = 0; k < l; ++k)
+        if (r.has_res && (*ls)[i + k].conv.hargs.out == Lk.conv.hargs.res) r.res_layer = k;
+      M.flops_per_img += Lk.flops_per_img; M.bytes_per_img += Lk.bytes_per_img;
+    }
+    const HaloKArgs& a = M.conv.hargs;
+    hc.n_layers = n;
+    hc.dep_target = a.tiles_w * a.tiles_h * a.n_tiles * 8;          // tiles of one image x 8 epilogue warps
+    int* d_dep = nullptr;
+    const size_t dep_bytes = ((size_t)n * a.n_img + 1) * sizeof(int);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_dep), dep_bytes));
+    dev_allocs->push_back(d_dep);
+    CUDA_TRY(cudaMemset(d_dep, 0, dep_bytes));
+    hc.dep = d_dep;
+    HaloChain* d_chain = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_chain), sizeof(HaloChain)));
+    dev_allocs->push_back(d_chain);
+    CUDA_TRY(cudaMemcpy(d_chain, &hc, sizeof(HaloChain), cudaMemcpyHostToDevice));
+    M.chain_len = n; M.d_chain = d_chain;
+    M.conv.smem = smem;
+    M.conv.grid = (unsigned)std::min((long long)n * a.total_tiles, (long long)num_sms());
+    { const char* e = getenv("UWM_CHAIN_GRID"); if (e && atoi(e) > 0) M.conv.grid = (unsigned)std::min<long long>(atoi(e), M.conv.grid); }
+    { const char* e = getenv("UWM_VERBOSE");
+      if (e && e[0] == '1') fprintf(stderr, "chain of %d layers: %s (tiles/layer %d, grid %u, dep target %d, smem %zu)\n", n,
+                                    M.name.c_str(), a.total_tiles, M.conv.grid, hc.dep_target, smem); }
+    out.push_back(M);
+    i = j;
+  }
+#ifdef UWM_BENCH_TOOLS
+  // trace one chain launch only (tools/gpu_trace_chain.py): every other launch of the plan loses its trace pointer
+  if (const char* e = getenv("UWM_TRACE_CHAIN")) {
+    int want = atoi(e), k = 0;
+    for (Launch& L : out) {
+      const bool keep = L.chain_len > 1 && k++ == want;
+      if (!keep) { L.conv.hargs.trace = nullptr; }
+    }
+  }
+#endif
+  ls->swap(out);
   return UWM_OK;
 }
 
@@ -1690,7 +1872,15 @@ static int run_launch(const Launch& L, cudaStream_t st) {
     case OP_PREP: return launch_prep(L.src, L.c, L.n, L.h, L.w, L.dst, st);
     case OP_POOL: return launch_maxpool(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
     case OP_CONV:
-    case OP_HEAD: return launch_conv(L.conv, st);
+    case OP_HEAD:
+      if (L.chain_len > 1) {
+        int rc = set_conv_attrs();
+        if (rc) return rc;
+        rc = chain_dispatch(&L.conv, L.d_chain, st);
+        if (rc) return rc;
+        return post_launch("conv_halo_kernel (chain)", st);
+      }
+      return launch_conv(L.conv, st);
   }
   return UWM_OK;
 }
@@ -1713,11 +1903,12 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
     // tensor maps and tile shapes depend on the batch only; the caller-owned pointers of the first (prep)
     // and last (head) kernels are patched per call
     Plan pl;
-    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &pl.launches);
-    if (rc) return rc;
+    rc = instantiate(m, d_in, in_fmt, batch, d_logits, apply_sigmoid, d_mask, thr_logit, &pl.launches, &pl.dev_allocs);
+    if (rc) { for (void* q : pl.dev_allocs) cudaFree(q); return rc; }
     pit = m->plans.emplace(batch, std::move(pl)).first;
   }
   Plan& pl = pit->second;
+  m->last_plan_launches = (int)pl.launches.size();
   Launch& first = pl.launches.front();
   Launch& last = pl.launches.back();
   first.src = d_in; first.c = in_fmt;
@@ -1835,7 +2026,9 @@ extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::vector<Launch> ls;
-  rc = instantiate(m, d_in, in_fmt, batch, d_logits, 0, d_mask, thr_logit, &ls);
+  std::vector<void*> allocs;
+  struct FreeAll { std::vector<void*>* v; ~FreeAll() { for (void* q : *v) cudaFree(q); } } free_all{&allocs};
+  rc = instantiate(m, d_in, in_fmt, batch, d_logits, 0, d_mask, thr_logit, &ls, &allocs);
   if (rc) return rc;
   const int n = (int)ls.size();
   if (n > n_max) return fail(UWM_EINVAL, "profile: need room for %d kernels", n);
@@ -1850,9 +2043,9 @@ extern "C" int uwm_model_profile(uwm_model* m, const void* d_in, int in_fmt, int
   CUDA_TRY(cudaStreamSynchronize(st));
   for (int i = 0; i < n; ++i) {
     CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-    snprintf(names + (size_t)i * 64, 64, "%s", m->ops[i].name.c_str());
-    if (flops) flops[i] = m->ops[i].flops_per_img * batch;
-    if (bytes) bytes[i] = m->ops[i].bytes_per_img * batch;
+    snprintf(names + (size_t)i * 64, 64, "%s", ls[i].name.c_str());
+    if (flops) flops[i] = ls[i].flops_per_img * batch;
+    if (bytes) bytes[i] = ls[i].bytes_per_img * batch;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return n;
