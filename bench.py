@@ -42,6 +42,10 @@ CONFIGS = {
             metric="images/sec UNet-ResNet34 1024x1024 bf16 mask inference",
             workload="configs[2]: smp Unet resnet34, 1024x1024, batch 64 TOTAL split data-parallel over the GPUs "
                      "(64/N images per GPU), bf16 inference, sigmoid+threshold uint8 mask"),
+    5: dict(encoder="resnet34", size=512, batch=16, scaling="weak", train=True,
+            metric="images/sec UNet-ResNet34 512x512 training step (Dice+BCE, Adam, gradient all-reduce)",
+            workload="configs[4]: smp Unet resnet34, 512x512, batch 16 per GPU, training step with Dice+BCE loss and NCCL "
+                     "gradient allreduce"),
     4: dict(encoder="resnet50", size=768, batch=32, scaling="weak",
             metric="images/sec UNet-ResNet50 768x768 bf16 mask inference",
             workload="configs[3]: smp Unet resnet50, 768x768, batch 32 per GPU, bf16 inference, sigmoid+threshold uint8 mask"),
@@ -181,11 +185,157 @@ def gpu_control_run(dev, u8_batch, steps: int):
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
+def cpu_train_reference_run(steps: int, warmup: int, images_per_step: int):
+    """Config 5 on the host cores: the oracle module trained the reference's way (train mode, Dice+BCE, Adam)."""
+    import torch
+    from oracle import unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build(ENCODER, seed=0, random_bn=True).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    x = O.image_like_input(images_per_step, SIZE, seed=1)
+    t = (torch.rand(images_per_step, 1, SIZE, SIZE, generator=torch.Generator().manual_seed(2)) > 0.85).float()
+
+    def step():
+        opt.zero_grad()
+        loss = O.dice_bce_loss(model(x), t)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return images_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_train(args):
+    """BASELINE configs[4]: one optimisation step per 'step' (forward in train mode on the tcgen05 conv kernels,
+    Dice+BCE, torch-autograd backward, bucketed NCCL gradient all-reduce overlapped with the backward, Adam)."""
+    import torch
+    import torch.distributed as dist
+    from unet_watermark_b200 import _lib
+    from unet_watermark_b200.training import TrainStep
+    from unet_watermark_b200.unet_model import Unet
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    select_config(5, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    lib = _lib.load()
+    torch.manual_seed(0)                                   # identical replicas on every rank
+    model = Unet(ENCODER, encoder_weights=None).to(dev)
+    ts = TrainStep(model)
+    n_pool = 4
+    gi = torch.Generator().manual_seed(100 + rank)
+    host_x = [torch.randn(BATCH, 3, SIZE, SIZE, generator=gi).pin_memory() for _ in range(n_pool)]
+    host_t = [(torch.rand(BATCH, SIZE, SIZE, generator=gi) > 0.85).long().pin_memory() for _ in range(n_pool)]   # long {0,1} masks (src/utils/dataset.py:119-122)
+    dev_x = [h.to(dev) for h in host_x]
+    dev_t = [h.to(dev) for h in host_t]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        ts.step(dev_x[i % n_pool], dev_t[i % n_pool])
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.uwm_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    exposed = []
+    for i in range(args.steps):
+        loss = ts.step(dev_x[i % n_pool], dev_t[i % n_pool], time_exchange=True)
+        exposed.append(ts._pending)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = int(lib.uwm_kernel_launch_count() - l0)
+    ms_total = e0.elapsed_time(e1)
+    exposed_ms = sum(a.elapsed_time(b) for a, b in exposed) / max(len(exposed), 1)
+    final_loss = float(loss)
+    # end to end: every step uploads its images + masks from pinned host memory and reads the loss back (loss.item(), :107)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        x = host_x[i % n_pool].to(dev, non_blocking=True)
+        t = host_t[i % n_pool].to(dev, non_blocking=True)
+        _ = ts.step(x, t).item()
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_e2e, exposed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e, exposed_ms = (float(v) for v in tt)
+    if rank == 0:
+        eng_flops = 62.512e9 * (SIZE / 512.0) ** 2            # forward conv FLOPs per image (SURVEY.md App. B)
+        value = world * BATCH * args.steps / (ms_total * 1e-3)
+        tf = value * 3.0 * eng_flops / 1e12 / world            # forward + backward ~ 3x forward (SURVEY.md §8d)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": SCALING, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "baseline_config": 5, "encoder": ENCODER, "image": [SIZE, SIZE],
+                           "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                           "loss": "0.5 * Dice(smooth 1e-5) + 0.5 * BCEWithLogits", "optimizer": "Adam lr 1e-4 wd 1e-4",
+                           "forward": "tcgen05 conv kernels (all convs but the 3-channel stem and the 1-channel head) + train-mode BatchNorm",
+                           "backward": "torch autograd (aten.convolution_backward)",
+                           "l2": f"inputs rotate through {n_pool} batches of {BATCH * 3 * SIZE * SIZE * 4 / 1e6:.0f} MB > 126 MB L2"},
+                "tflops_per_gpu_3x_forward": tf, "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
+                "allreduce": {"bytes_per_step": ts.buckets.bytes, "buckets": len(ts.buckets.buckets),
+                              "exposed_ms_per_step": exposed_ms,
+                              "how": "CUDA events between the end of the backward and the last averaged bucket, mean per step, max over ranks"},
+                "e2e": {"value": world * BATCH * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": world * BATCH * SIZE * SIZE * (3 * 4 + 8), "d2h_bytes_per_step": world * 4,
+                        "ms_per_step": ms_e2e / args.steps,
+                        "api": "pinned host fp32 images + int64 masks -> H2D -> TrainStep.step -> loss.item()"},
+                "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
+                "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel / conv_tc_kernel (forward convs of the training step)",
+                             "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+                             "traffic": None, "peak_source": peaks["source"] + ", burst figure",
+                             "how": "3 x forward conv FLOPs per image x images/s (whole step incl. torch backward, BatchNorm and Adam)"}}
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_train_reference_run(steps=2, warmup=1, images_per_step=2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "2 timed training steps x 2 images, fp32, oracle module, all host threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     select_config(args.config, int(os.environ.get("WORLD_SIZE", "1")))
+    if args.config == 5:
+        v, ms, cores = cpu_train_reference_run(args.steps, max(args.warmup, 1), 2)
+        sample = f"2 of {BATCH} images per training step, fp32, oracle module trained the reference's way, {cores} threads"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": SCALING, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": WORKLOAD, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return 0
     per_step = 2 if SIZE <= 512 else 1
     v, ms, cores = cpu_reference_run(args.steps, max(args.warmup, 1), per_step)
     sample = f"{per_step} of {BATCH} images per step, fp32, oracle port of the reference CPU path, {cores} threads"
@@ -478,10 +628,12 @@ def main():
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--config", type=int, choices=sorted(CONFIGS), default=2,
                     help="BASELINE.json config (1-based): 2 = r34 512 B16 (default line), 3 = r34 1024 B64 split over the GPUs, "
-                         "4 = r50 768 B32")
+                         "4 = r50 768 B32, 5 = r34 512 B16 training step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 5:
+        return run_train(args)
     return run_ours(args)
 
 

@@ -149,3 +149,47 @@ def test_cli_surface():
     a = p.parse_args(["predict", "--sigmoid", "--threshold", "0.3", "--batch-size", "4"])
     assert a.sigmoid and a.threshold == 0.3 and a.batch_size == 4
     assert p.parse_args(["predict", "--no-sigmoid"]).sigmoid is False      # compat flag, default convention
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch.nn as nn
+    from unet_watermark_b200.training import GradBuckets
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                           # identical replicas
+    net = nn.Sequential(nn.Linear(7, 5), nn.ReLU(), nn.Linear(5, 3), nn.ReLU(), nn.Linear(3, 1))
+    buckets = GradBuckets(net.parameters(), bucket_mb=1e-4)        # ~26 floats per bucket: several buckets
+    g = torch.Generator().manual_seed(100 + rank)                  # different data per rank
+    x, y = torch.randn(6, 7, generator=g), torch.randn(6, 1, generator=g)
+    buckets.zero_grad()
+    ((net(x) - y) ** 2).mean().backward()
+    local = [p.grad.flatten().tolist() for p in net.parameters()]      # plain lists: they cross process boundaries
+    buckets.finish()
+    avg = [p.grad.flatten().tolist() for p in net.parameters()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    if rank == 0:
+        q.put((len(buckets.buckets), avg, gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bucketed_gradient_allreduce_averages():
+    """The exchange step of the optional training path (config 5): every rank ends with the mean gradient."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n_buckets, avg, gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n_buckets >= 2
+    for i, a in enumerate(avg):
+        want = (torch.tensor(gathered[0][i]) + torch.tensor(gathered[1][i])) / 2
+        assert torch.allclose(torch.tensor(a), want, atol=1e-6)
+    assert any(gathered[0][i] != gathered[1][i] for i in range(len(avg)))      # the ranks really saw different data

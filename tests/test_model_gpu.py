@@ -143,9 +143,9 @@ def test_errors_match_reference_contract(cuda_device):
         m(torch.zeros(1, 3, 100, 64, device=cuda_device))
     with pytest.raises(RuntimeError, match="no CPU"):
         m(torch.zeros(1, 3, 64, 64))
-    m.train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 64, 64, device=cuda_device))
+    m.train()                                      # train mode has its own path (tests/test_training_gpu.py), also CUDA-only
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(1, 3, 64, 64))
 
 
 def test_weights_reload_after_load_state_dict(cuda_device):

@@ -1,0 +1,93 @@
+"""BASELINE config 5 (optional training step): our train-mode forward (tcgen05 convs + train-mode BatchNorm) and the
+torch-autograd backward against the fp32 oracle trained the same way (reference src/train.py:82-107 semantics:
+model.train(), Dice+BCE composition, Adam)."""
+import copy
+
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from tests.fixtures import synthetic_watermark_batch
+from unet_watermark_b200 import _lib
+from unet_watermark_b200.losses import CombinedLoss, DiceLoss, dice_bce_from_config
+from unet_watermark_b200.config import get_cfg_defaults
+from unet_watermark_b200.training import TrainStep
+from unet_watermark_b200.unet_model import Unet
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(dev, seed=0):
+    ref = O.build("resnet34", seed=seed, random_bn=True).to(dev).train()
+    m = Unet("resnet34", encoder_weights=None)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    return ref, m.to(dev).train()
+
+
+def test_losses_equal_oracle_restatement(cuda_device):
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(3, 1, 32, 32, generator=g).to(cuda_device)
+    target = (torch.rand(3, 1, 32, 32, generator=g) > 0.7).long().to(cuda_device)
+    cfg = get_cfg_defaults()
+    assert abs(float(dice_bce_from_config(cfg)(logits, target)) - float(O.dice_bce_loss(logits, target.float()))) < 1e-6
+    assert abs(float(DiceLoss(smooth=1e-5)(logits, target)) - float(O.dice_loss_binary(logits, target.float()))) < 1e-6
+    assert float(DiceLoss(smooth=1e-5)(logits, torch.zeros_like(target))) == 0.0
+    assert isinstance(dice_bce_from_config(cfg), CombinedLoss)
+
+
+def test_train_mode_forward_backward_match_oracle(cuda_device):
+    ref, m = _pair(cuda_device)
+    x, _, t = synthetic_watermark_batch(4, 128, seed=3, device=cuda_device)
+    before = _lib.load().uwm_kernel_launch_count()
+    y = m(x)
+    assert _lib.load().uwm_kernel_launch_count() - before >= 40          # the convs ran on the tcgen05 kernel
+    assert y.requires_grad and y.shape == (4, 1, 128, 128) and y.dtype == torch.float32
+    y32 = ref(x)
+    d = (y.detach() - y32.detach()).abs()
+    assert d.max() <= 0.12 * y32.abs().max() and d.mean() <= 0.06 * y32.std(), (d.max().item(), d.mean().item())
+    loss, loss32 = O.dice_bce_loss(y, t), O.dice_bce_loss(y32, t)
+    assert abs(float(loss) - float(loss32)) <= 0.03 * abs(float(loss32)) + 1e-3
+    loss.backward()
+    loss32.backward()
+    cos_all, n = 0.0, 0
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and p.grad.shape == q.grad.shape, k
+        if q.grad.norm() > 0:
+            c = torch.nn.functional.cosine_similarity(p.grad.flatten().float(), q.grad.flatten(), dim=0).item()
+            cos_all += c; n += 1
+            if p.numel() > 10000:
+                assert c > 0.9, (k, c)
+    assert cos_all / n > 0.95, cos_all / n
+    # train-mode BatchNorm updated the running statistics like the oracle's
+    for (k, b), (_, b32) in zip(m.named_buffers(), ref.named_buffers()):
+        if k.endswith("running_mean"):
+            assert (b - b32).abs().max() <= 0.05 * b32.abs().max() + 0.02, k
+        if k.endswith("num_batches_tracked"):
+            assert int(b) == int(b32) == 1
+
+
+def test_train_steps_reduce_the_loss_and_eval_path_sees_new_weights(cuda_device):
+    torch.manual_seed(0)
+    m = Unet("resnet34", encoder_weights=None).to(cuda_device)
+    ts = TrainStep(m, lr=1e-3)
+    losses = []
+    for it in range(40):
+        x, _, t = synthetic_watermark_batch(8, 128, seed=500 + it, device=cuda_device)
+        losses.append(float(ts.step(x, t[:, 0].long())))
+    assert sum(losses[-5:]) / 5 < 0.8 * sum(losses[:5]) / 5, (losses[:5], losses[-5:])
+    # the inference plan re-folds BatchNorm from the trained parameters (weight generation tracking)
+    m.eval()
+    x, u8, t = synthetic_watermark_batch(4, 128, seed=999, device=cuda_device)
+    y_eval = m(x)
+    ref = O.Unet("resnet34").to(cuda_device)
+    ref.load_state_dict(m.state_dict())
+    ref.eval()
+    with torch.no_grad():
+        y32 = ref(x)
+    d = (y_eval - y32).abs()
+    assert d.max() <= 0.08 * y32.abs().max() + 0.05 and d.mean() <= 0.05 * y32.std() + 0.01
+    snapshot = copy.deepcopy(m.state_dict())
+    ts.step(x, t[:, 0].long())
+    m.eval()
+    assert not torch.equal(m(x), y_eval)                       # one more step changed the weights -> new plan weights
+    assert any(not torch.equal(v, snapshot[k]) for k, v in m.state_dict().items() if "num_batches" not in k)

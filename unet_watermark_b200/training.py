@@ -1,0 +1,219 @@
+"""Optional training step of the path (BASELINE.json configs[4]: Unet-resnet34, 512x512, batch 16 per GPU, Dice+BCE,
+NCCL gradient all-reduce).  Semantics source: reference src/train.py:68-127 (``train_epoch``: ``model.train()``,
+forward, loss, backward, optimizer step), :265-277 (Adam(lr, weight_decay)), src/utils/losses.py, src/configs/config.py.
+
+What runs where
+  forward   every convolution whose channel counts are multiples of 16 (all but the 3-channel stem and the 1-channel
+            head) runs on the hand-written tcgen05 implicit-GEMM kernel through the C ABI (``uwm_conv2d_nhwc_bf16``:
+            bf16 NHWC, fp32 accumulation), as a ``torch.autograd.Function``.  BatchNorm runs in TRAIN mode (batch
+            statistics, running-stat update) - so it cannot be folded into the conv as the inference plan does - through
+            the model's own ``nn.BatchNorm2d`` modules; ReLU / max-pool / nearest-upsample / concat are torch ops.
+  backward  torch autograd: ``aten.convolution_backward`` (cuDNN dgrad / wgrad) on the saved bf16 tensors.  Hand-written
+            dgrad / wgrad kernels are the next step, not part of this round.
+  exchange  :class:`GradBuckets` - flat fp32 gradient buckets (parameters own views into them) all-reduced over NCCL
+            as soon as the backward pass has produced every gradient of a bucket, overlapping the rest of the backward;
+            the exposed part (the wait after the backward) is measured with CUDA events.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = conv2d(x, w) (no bias) on the tcgen05 kernel; x, y: NCHW-shaped channels_last bf16 tensors."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding):
+        w16 = weight.detach().to(torch.bfloat16)
+        xn = x.detach().permute(0, 2, 3, 1)                       # NHWC view of the channels_last tensor
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        cout, _, kh, kw = weight.shape
+        wp = w16.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()   # UWM_PACK_TAPS ([cout][kh*kw][cin]), packed on the device
+        zero = torch.zeros(cout, dtype=torch.float32, device=x.device)
+        y = ops.conv2d(xn, wp, zero, kh, kw, stride, padding, relu=False)
+        ctx.save_for_backward(x, w16)
+        ctx.conf = (stride, padding)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w16 = ctx.saved_tensors
+        stride, padding = ctx.conf
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            gy, x, w16.contiguous(memory_format=torch.channels_last), None, [stride, stride], [padding, padding], [1, 1],
+            False, [0, 0], 1, [ctx.needs_input_grad[0], True, False])
+        return gx, gw.float() if gw is not None else None, None, None
+
+
+def _conv(x: torch.Tensor, m: nn.Conv2d) -> torch.Tensor:
+    cout, cin = m.weight.shape[:2]
+    if cin % 16 == 0 and cout % 16 == 0 and m.bias is None:
+        return _ConvFn.apply(x, m.weight, m.stride[0], m.padding[0])
+    # 3-channel stem / 1-channel head: not expressible on the 16-channel-granular single-operator ABI
+    return F.conv2d(x, m.weight.to(x.dtype), None if m.bias is None else m.bias.to(x.dtype), m.stride, m.padding)
+
+
+def _bn_relu(x, bn: nn.BatchNorm2d, relu: bool = True):
+    y = bn(x)                                                       # train mode: batch statistics + running-stat update
+    return F.relu(y) if relu else y
+
+
+def forward_train(model, x: torch.Tensor) -> torch.Tensor:
+    """smp ``Unet.forward`` with BatchNorm in the module's current mode and autograd enabled.
+    x: fp32 [B,3,H,W] (ImageNet-normalised) -> fp32 logits [B,1,H,W]."""
+    if not x.is_cuda:
+        raise RuntimeError("unet_watermark_b200 trains on CUDA (sm_100a) only; there is no CPU fallback")
+    model.check_input_shape(x.shape[-2], x.shape[-1])
+    enc = model.encoder
+    y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = _bn_relu(_conv(y, enc.conv1), enc.bn1)
+    feats = [y]
+    y = F.max_pool2d(y, 3, 2, 1)
+    for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
+        for blk in layer:
+            idt = y
+            if blk.downsample is not None:
+                idt = _bn_relu(_conv(y, blk.downsample[0]), blk.downsample[1], relu=False)
+            if hasattr(blk, "conv3"):                               # Bottleneck
+                t = _bn_relu(_conv(y, blk.conv1), blk.bn1)
+                t = _bn_relu(_conv(t, blk.conv2), blk.bn2)
+                y = F.relu(_bn_relu(_conv(t, blk.conv3), blk.bn3, relu=False) + idt)
+            else:                                                   # BasicBlock
+                t = _bn_relu(_conv(y, blk.conv1), blk.bn1)
+                y = F.relu(_bn_relu(_conv(t, blk.conv2), blk.bn2, relu=False) + idt)
+        feats.append(y)
+    skips = feats[::-1]                                             # layer4, layer3, layer2, layer1, stem
+    y = skips[0]
+    for i, blk in enumerate(model.decoder.blocks):
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+        if i + 1 < len(skips):
+            y = torch.cat([y, skips[i + 1]], dim=1)                 # upsampled first, skip second
+        y = y.contiguous(memory_format=torch.channels_last)
+        y = _bn_relu(_conv(y, blk.conv1[0]), blk.conv1[1])
+        y = _bn_relu(_conv(y, blk.conv2[0]), blk.conv2[1])
+    logits = _conv(y, model.segmentation_head[0]).float()
+    if model.activation_name == "sigmoid":
+        logits = torch.sigmoid(logits)
+    return logits
+
+
+class GradBuckets:
+    """Bucketed gradient all-reduce overlapped with the backward pass.
+
+    Parameters are grouped, in reverse registration order (the order the backward produces their gradients), into
+    flat fp32 buckets of ~``bucket_mb``; ``p.grad`` is a view into its bucket, so autograd accumulates in place.  A
+    post-accumulate hook counts a bucket's finished gradients and launches ``all_reduce(async)`` on the last one.
+    ``finish()`` waits for the outstanding collectives and averages."""
+
+    def __init__(self, params, bucket_mb: float = 25.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._hooks = []
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        cur: List[torch.nn.Parameter] = []
+        n = 0
+        groups = []
+        for p in reversed(self.params):
+            if cur and n + p.numel() > cap:
+                groups.append(cur); cur, n = [], 0
+            cur.append(p); n += p.numel()
+        if cur:
+            groups.append(cur)
+        for bi, g in enumerate(groups):
+            flat = torch.zeros(sum(p.numel() for p in g), dtype=torch.float32, device=g[0].device)
+            off = 0
+            for p in g:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[p] = bi
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+            self.buckets.append(flat)
+        self._sizes = [len(g) for g in groups]
+        self._ready = [0] * len(groups)
+        self._works = []
+        self.bytes = sum(b.numel() * 4 for b in self.buckets)
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.zero_()
+        self._ready = [0] * len(self.buckets)
+        self._works = []
+
+    def _on_grad(self, p):
+        bi = self._bucket_of[p]
+        self._ready[bi] += 1
+        if self._ready[bi] == self._sizes[bi] and self.world > 1:
+            self._works.append(dist.all_reduce(self.buckets[bi], group=self.group, async_op=True))
+
+    def finish(self):
+        """Wait for every bucket's all-reduce and turn the sums into means."""
+        if self.world > 1:
+            for i, n in enumerate(self._ready):                  # parameters that received no gradient this step
+                if n != self._sizes[i]:
+                    self._works.append(dist.all_reduce(self.buckets[i], group=self.group, async_op=True))
+            for w in self._works:
+                w.wait()
+            for b in self.buckets:
+                b.div_(self.world)
+        self._works = []
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+class TrainStep:
+    """One optimisation step as the reference runs it (src/train.py:82-107), data-parallel over the process group."""
+
+    def __init__(self, model, cfg=None, lr: Optional[float] = None, weight_decay: Optional[float] = None,
+                 criterion: Optional[nn.Module] = None, bucket_mb: float = 25.0):
+        from .config import get_cfg_defaults
+        from .losses import dice_bce_from_config
+        self.cfg = cfg if cfg is not None else get_cfg_defaults()
+        self.model = model
+        self.criterion = criterion if criterion is not None else dice_bce_from_config(self.cfg)
+        # reference src/train.py:265-270: Adam(lr = TRAIN.LR, weight_decay = TRAIN.WEIGHT_DECAY)
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=self.cfg.TRAIN.LR if lr is None else lr,
+                                          weight_decay=self.cfg.TRAIN.WEIGHT_DECAY if weight_decay is None else weight_decay)
+        self.buckets = GradBuckets(model.parameters(), bucket_mb=bucket_mb)
+        self.exposed_ms: List[float] = []
+
+    def step(self, images: torch.Tensor, masks: torch.Tensor, time_exchange: bool = False) -> torch.Tensor:
+        """images: fp32 [B,3,H,W] normalised; masks: {0,1} [B,H,W] or [B,1,H,W].  Returns the (detached) loss."""
+        self.model.train()
+        self.buckets.zero_grad()                                   # optimizer.zero_grad(): grads are bucket views
+        out = self.model(images)
+        if masks.dim() == 3:
+            masks = masks.unsqueeze(1)
+        loss = self.criterion(out, masks)
+        loss.backward()
+        if time_exchange and images.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.buckets.finish()
+            e1.record()
+            self._pending = (e0, e1)
+        else:
+            self.buckets.finish()
+        self.optimizer.step()
+        return loss.detach()
+
+    def exposed_exchange_ms(self) -> float:
+        """Device time between the end of the backward pass and the last averaged bucket of the latest step timed with
+        ``time_exchange=True`` (the part of the all-reduce the backward did not hide)."""
+        e0, e1 = self._pending
+        e1.synchronize()
+        return e0.elapsed_time(e1)

@@ -268,8 +268,7 @@ class Unet(nn.Module):
             raise RuntimeError("unet_watermark_b200.Unet runs only on CUDA (sm_100a) tensors; there is no CPU "
                                "fallback. Move the model and the input to a B200 (`.to('cuda')`).")
         if self.training:
-            raise NotImplementedError("unet_watermark_b200.Unet.forward implements eval-mode inference "
-                                      "(BatchNorm folded); call model.eval() — see train_step for training")
+            raise RuntimeError("internal: the inference plan (BatchNorm folded) was reached in train mode")
         if x.dtype == torch.uint8:
             if x.dim() != 4 or x.shape[-1] != 3:
                 raise ValueError("uint8 input must be NHWC RGB [B,H,W,3]")
@@ -287,9 +286,15 @@ class Unet(nn.Module):
                                apply_sigmoid=(self.activation_name == "sigmoid" or force_sigmoid),
                                use_graph=self.use_cuda_graph, mask_out=mask_out)
 
-    @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        logits, _ = self._run(x, True, None, True)
+        """eval mode: the fused inference plan (BatchNorm folded, no autograd), as the reference runs it under
+        ``model.eval()`` + ``torch.no_grad()``.  train mode (reference src/train.py:70,89): BatchNorm with batch
+        statistics and autograd enabled - the convolutions still run on the tcgen05 kernels (training.py)."""
+        if self.training:
+            from .training import forward_train
+            return forward_train(self, x)
+        with torch.no_grad():
+            logits, _ = self._run(x, True, None, True)
         return logits
 
     @torch.no_grad()
