@@ -201,7 +201,7 @@ def cpu_train_reference_run(steps: int, warmup: int, images_per_step: int):
         loss = O.dice_bce_loss(model(x), t)
         loss.backward()
         opt.step()
-        return float(loss)
+        return loss.item()
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
