@@ -892,6 +892,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
         // them into the image's counter of this layer.  The stores went through the async proxy: wait for their
         // completion (not just for the smem read), then a proxy fence, then the release.
         bulk_wait_done<0>();
+        if (warp == 2) halo_trace(p, 560 + it);                 // trace: this warp's stores of the tile are complete
         fence_proxy_async_all();
         red_release_gpu_add(chain->dep + layer * p.n_img + t.img, 1);
       }

@@ -1854,6 +1854,10 @@ static int merge_chains(std::vector<Launch>* ls, std::vector<void*>* dev_allocs)
   }
 #ifdef UWM_BENCH_TOOLS
   // trace one chain launch only (tools/gpu_trace_chain.py): every other launch of the plan loses its trace pointer
+  if (const char* e = getenv("UWM_TRACE_LAUNCH")) {       // trace the k-th launch of the plan only
+    int want = atoi(e), k = 0;
+    for (Launch& L : out) { if (k++ != want) L.conv.hargs.trace = nullptr; else fprintf(stderr, "tracing launch %d: %s\n", want, L.name.c_str()); }
+  } else
   if (const char* e = getenv("UWM_TRACE_CHAIN")) {
     int want = atoi(e), k = 0;
     for (Launch& L : out) {
