@@ -300,6 +300,11 @@ int uwm_mask_components(const uint8_t* d_masks, const uwm_image_desc* h_desc, co
                         int32_t* d_labels, int32_t* d_area, int32_t* d_order, int32_t* d_bbox, void* d_workspace,
                         size_t workspace_bytes, void* stream);
 
+/* d_out[i] = {foreground pixels, 8-connected components, area of the largest component} of mask i - the statistics
+ * reference src/scripts/model_selector.py:171-197 takes from cv2.connectedComponentsWithStats. */
+int uwm_mask_component_summary(const uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n,
+                               int32_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- bench tools: exported only by the tools build of the library (-DUWM_BENCH_TOOLS; python -m
  * unet_watermark_b200.build --tools -> lib/libuwm_b200_tools.so).  The product library has none of these, nor the
  * UWM_DBG pipeline-isolation switches. ---- */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "uwm_mask_text_features": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint, _P, _P, C.c_size_t, _P]),
     "uwm_mask_morphology": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "uwm_mask_components": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "uwm_mask_component_summary": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
 }
 
 # exported only by the tools build (-DUWM_BENCH_TOOLS); bound when present

@@ -404,6 +404,20 @@ __global__ void __launch_bounds__(256) ccl_text_features_kernel(const CclImg* __
   }
 }
 
+// per image: {foreground pixels, components, largest component area} (reference src/scripts/model_selector.py:171-197)
+__global__ void __launch_bounds__(256) ccl_summary_kernel(const CclImg* __restrict__ ci, const int* __restrict__ labels,
+                                                          const int* __restrict__ area, int* __restrict__ out /* [n][3] */) {
+  const CclImg c = ci[blockIdx.y];
+  const long long total = (long long)c.w * c.h;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    if (labels[c.pix_off + idx] != (int)idx) continue;            // roots only
+    const int a = area[c.pix_off + idx];
+    atomicAdd(&out[3 * blockIdx.y + 0], a);
+    atomicAdd(&out[3 * blockIdx.y + 1], 1);
+    atomicMax(&out[3 * blockIdx.y + 2], a);
+  }
+}
+
 unsigned grid_x(long long items, int threads = 256) {
   const long long blocks = (items + threads - 1) / threads;
   return (unsigned)std::max(1LL, std::min(blocks, 148LL * 8));
@@ -703,4 +717,23 @@ extern "C" int uwm_mask_components(const uint8_t* d_masks, const uwm_image_desc*
   c.labels = d_labels; c.area = d_area; c.order = d_order; c.bbox = d_bbox;
   run_ccl(c, c.b0, d_bbox != nullptr);
   return ipost("mask component kernels", c.launches + 1);
+}
+
+// d_out[i] = {foreground pixels, 8-connected components, area of the largest component} of mask i
+// (cv2.connectedComponentsWithStats as reference src/scripts/model_selector.py:171-197 uses it)
+extern "C" int uwm_mask_component_summary(const uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc,
+                                          int n, int32_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!d_masks || !d_desc || !d_out || !d_workspace) return ifail(UWM_EINVAL, "mask_component_summary: null pointer");
+  int rc = check_descs(h_desc, n, "mask_component_summary");
+  if (rc) return rc;
+  PostCtx c;
+  rc = post_setup(c, h_desc, n, d_workspace, workspace_bytes, false, stream);
+  if (rc) return rc;
+  dim3 gw(grid_x(c.g.max_words * 32), n);
+  pack_bits_kernel<<<gw, 256, 0, c.st>>>(d_masks, d_desc, c.d_bi, c.b0);
+  run_ccl(c, c.b0, false);
+  cudaMemsetAsync(d_out, 0, 12 * (size_t)n, c.st);
+  dim3 gp(grid_x(c.g.max_pixels), n);
+  ccl_summary_kernel<<<gp, 256, 0, c.st>>>(c.d_ci, c.labels, c.area, d_out);
+  return ipost("mask component summary kernels", c.launches + 2);
 }

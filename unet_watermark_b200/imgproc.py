@@ -207,3 +207,16 @@ def mask_components(masks: torch.Tensor, batch: RaggedBatch, want_bbox: bool = T
                                                    bbox.data_ptr() if bbox is not None else None, ws.data_ptr(),
                                                    ws.numel(), _stream(masks)), "uwm_mask_components")
     return labels, area, order, bbox
+
+
+def mask_component_summary(masks: torch.Tensor, batch: RaggedBatch) -> List[Tuple[int, int, int]]:
+    """Per mask: (foreground pixels, 8-connected components, largest component area) - the statistics the reference's
+    model_selector takes from ``cv2.connectedComponentsWithStats`` (src/scripts/model_selector.py:171-197)."""
+    _need_cuda(masks, "mask_component_summary")
+    ws = _workspace(batch, masks.device)
+    out = torch.empty(batch.n, 3, dtype=torch.int32, device=masks.device)
+    with torch.cuda.device(masks.device):
+        _lib.check(_lib.load().uwm_mask_component_summary(masks.data_ptr(), batch.h_ptr, batch.d_ptr, batch.n, out.data_ptr(),
+                                                          ws.data_ptr(), ws.numel(), _stream(masks)),
+                   "uwm_mask_component_summary")
+    return [tuple(r) for r in out.cpu().tolist()]

@@ -217,9 +217,13 @@ class WatermarkPredictor:
 
     # -- one batch on the GPU ----------------------------------------------------------------------
     def _masks_for_images(self, images_bgr: List[np.ndarray], threshold: float, slot: int = 0,
-                          mask_types: Optional[List[str]] = None, pool: Optional[ThreadPoolExecutor] = None
-                          ) -> Tuple[List[np.ndarray], List[str]]:
-        """BGR uint8 images of arbitrary sizes -> (uint8 {0,255} masks at the original sizes, mask types used)."""
+                          mask_types: Optional[List[str]] = None, pool: Optional[ThreadPoolExecutor] = None,
+                          morphology: Optional[Sequence[Tuple[int, int, Tuple[int, int], int]]] = None,
+                          sigmoid: Optional[bool] = None) -> Tuple[List[np.ndarray], List[str]]:
+        """BGR uint8 images of arbitrary sizes -> (uint8 {0,255} masks at the original sizes, mask types used).
+        ``morphology``: a list of (op, shape, ksize, iterations) cv2-morphology steps run on the GPU INSTEAD of the
+        reference predictor's ``_optimize_mask`` (the other callers of the seam post-process differently, e.g.
+        reference src/scripts/watermark_filter.py:159-166); ``sigmoid`` overrides the predictor's convention."""
         n = len(images_bgr)
         s = self.img_size
         dev = self.device
@@ -242,12 +246,16 @@ class WatermarkPredictor:
             src.to(dev, stream_non_blocking=True)
             # 2. resize to the network size (bit-exact cv2 INTER_LINEAR; BGR -> RGB in the read), forward
             x = imgproc.resize_bilinear_u8(packed, src, s, s, swap_rb=True)
-            maps = self.model.predict_proba(x) if self.sigmoid else self.model(x)           # fp32 [n,1,S,S]
+            use_sigmoid = self.sigmoid if sigmoid is None else sigmoid
+            maps = self.model.predict_proba(x) if use_sigmoid else self.model(x)           # fp32 [n,1,S,S]
             # 3. bilinear upscale to every original size + threshold -> packed uint8 masks
             dst = imgproc.RaggedBatch(sizes, channels=1, device=dev)
             masks = imgproc.mask_upscale_threshold(maps, dst, threshold)
             types = list(mask_types) if mask_types is not None else [self.mask_type] * n
-            if self.post_process:
+            if morphology is not None:
+                for op, shape, ksize, iters in morphology:
+                    imgproc.mask_morphology(masks, dst, op, shape, ksize, iters)
+            elif self.post_process:
                 ws = None
                 if any(t == "auto" for t in types):
                     # reference _detect_watermark_type: geometric score on the GPU, Canny/Sobel statistics on CPU threads
