@@ -204,6 +204,65 @@ class Unet(nn.Module):
         return self.segmentation_head(self.decoder(*feats))
 
 
+class UnetPlusPlusDecoder(nn.Module):
+    """smp ``UnetPlusPlusDecoder`` (decoders/unetplusplus/decoder.py), restated: nested dense skip pathways.
+    Blocks ``x_{depth}_{layer}``; known answer 26 078 609 parameters for resnet34 (tests/test_oracle.py)."""
+
+    def __init__(self, encoder_channels: Sequence[int], decoder_channels: Sequence[int], n_blocks: int = 5):
+        super().__init__()
+        if n_blocks != len(decoder_channels):
+            raise ValueError(f"Model depth is {n_blocks}, but you provide `decoder_channels` for "
+                             f"{len(decoder_channels)} blocks.")
+        enc = list(encoder_channels[1:])[::-1]
+        self.in_channels = [enc[0]] + list(decoder_channels[:-1])
+        self.skip_channels = list(enc[1:]) + [0]
+        self.out_channels = list(decoder_channels)
+        self.center = nn.Identity()
+        blocks = {}
+        for layer_idx in range(len(self.in_channels) - 1):
+            for depth_idx in range(layer_idx + 1):
+                if depth_idx == 0:
+                    in_ch = self.in_channels[layer_idx]
+                    skip_ch = self.skip_channels[layer_idx] * (layer_idx + 1)
+                    out_ch = self.out_channels[layer_idx]
+                else:
+                    out_ch = self.skip_channels[layer_idx]
+                    skip_ch = self.skip_channels[layer_idx] * (layer_idx + 1 - depth_idx)
+                    in_ch = self.skip_channels[layer_idx - 1]
+                blocks[f"x_{depth_idx}_{layer_idx}"] = DecoderBlock(in_ch, skip_ch, out_ch)
+        blocks[f"x_{0}_{len(self.in_channels) - 1}"] = DecoderBlock(self.in_channels[-1], 0, self.out_channels[-1])
+        self.blocks = nn.ModuleDict(blocks)
+        self.depth = len(self.in_channels) - 1
+
+    def forward(self, *features: torch.Tensor) -> torch.Tensor:
+        features = list(features[1:])[::-1]
+        dense_x = {}
+        for layer_idx in range(len(self.in_channels) - 1):
+            for depth_idx in range(self.depth - layer_idx):
+                if layer_idx == 0:
+                    out = self.blocks[f"x_{depth_idx}_{depth_idx}"](features[depth_idx], features[depth_idx + 1])
+                    dense_x[f"x_{depth_idx}_{depth_idx}"] = out
+                else:
+                    dense_l_i = depth_idx + layer_idx
+                    cat = [dense_x[f"x_{idx}_{dense_l_i}"] for idx in range(depth_idx + 1, dense_l_i + 1)]
+                    cat = torch.cat(cat + [features[dense_l_i + 1]], dim=1)
+                    dense_x[f"x_{depth_idx}_{dense_l_i}"] = self.blocks[f"x_{depth_idx}_{dense_l_i}"](
+                        dense_x[f"x_{depth_idx}_{dense_l_i - 1}"], cat)
+        dense_x[f"x_{0}_{self.depth}"] = self.blocks[f"x_{0}_{self.depth}"](dense_x[f"x_{0}_{self.depth - 1}"])
+        return dense_x[f"x_{0}_{self.depth}"]
+
+
+class UnetPlusPlus(Unet):
+    """Restatement of ``smp.UnetPlusPlus`` (the reference's default MODEL.NAME, src/configs/config.py:15): the Unet
+    encoder and head with the nested decoder."""
+
+    def __init__(self, encoder_name: str = "resnet34", decoder_channels: Sequence[int] = (256, 128, 64, 32, 16), **kw):
+        super().__init__(encoder_name, decoder_channels=decoder_channels, **kw)
+        self.decoder = UnetPlusPlusDecoder(self.encoder.out_channels, list(decoder_channels), n_blocks=5)
+        self.name = f"unetplusplus-{encoder_name}"
+        _init_decoder(self.decoder)
+
+
 # ----------------------------------------------------------------------------------------------
 # bf16-emulating forward: the same arithmetic with the SAME quantisation points as the CUDA path
 # (BN folded in fp32, weights rounded once to bf16, every activation rounded once to bf16 after
@@ -361,9 +420,10 @@ def randomize_bn(model: nn.Module, seed: int = 0) -> nn.Module:
 
 
 def build(encoder_name="resnet34", decoder_channels=(256, 128, 64, 32, 16), seed: int = 0, random_bn: bool = False,
-          activation=None) -> Unet:
+          activation=None, arch: str = "Unet") -> Unet:
     torch.manual_seed(seed)
-    m = Unet(encoder_name, decoder_channels=decoder_channels, activation=activation)
+    cls = {"Unet": Unet, "UnetPlusPlus": UnetPlusPlus}[arch]
+    m = cls(encoder_name, decoder_channels=decoder_channels, activation=activation)
     if random_bn:
         randomize_bn(m, seed + 1)
     return m.eval()

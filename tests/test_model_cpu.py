@@ -30,7 +30,7 @@ def test_factory_surface_and_errors():
     with pytest.raises(ValueError, match="Unsupported model: Foo"):
         SMPModelFactory.create_model("Foo")
     with pytest.raises(NotImplementedError):
-        SMPModelFactory.create_model("UnetPlusPlus", encoder_weights=None)
+        SMPModelFactory.create_model("MAnet", encoder_weights=None)
     with pytest.raises(KeyError):
         SMPModelFactory.create_model("Unet", encoder_name="vgg16", encoder_weights=None)
     with pytest.raises(NotImplementedError):
@@ -111,3 +111,28 @@ def test_pack_stem_s2d_is_the_same_convolution():
     y = F.conv2d(F.pad(xs, (2, 1, 2, 1)), wp)                                           # taps -2..1
     assert y.shape == ref.shape
     assert torch.allclose(y, ref, atol=1e-3)
+
+
+def test_unetplusplus_reference_default_architecture_keys_and_known_answers():
+    """smp.UnetPlusPlus layout - 26 078 609 parameters for resnet34 (smp's published size), nested
+    block names x_{depth}_{layer}, strict state-dict exchange with the oracle restatement, reference default config."""
+    from oracle import unet_oracle as O
+    from unet_watermark_b200.config import get_cfg_defaults
+    from unet_watermark_b200.unet_model import create_model_from_config
+    cfg = get_cfg_defaults()                       # MODEL.NAME: UnetPlusPlus (reference src/configs/config.py:15)
+    cfg.MODEL.ENCODER_WEIGHTS = None
+    m = create_model_from_config(cfg)
+    assert type(m).__name__ == "UnetPlusPlus"
+    assert sum(p.numel() for p in m.parameters()) == 26_078_609
+    ref = O.build("resnet34", arch="UnetPlusPlus", seed=1, random_bn=True)
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys()) and len(m.state_dict()) == 350
+    m.load_state_dict(ref.state_dict(), strict=True)
+    names = sorted(k for k in m.decoder.blocks.keys())
+    assert names == sorted(["x_0_0", "x_0_1", "x_1_1", "x_0_2", "x_1_2", "x_2_2", "x_0_3", "x_1_3", "x_2_3", "x_3_3", "x_0_4"])
+    assert m.decoder.blocks["x_0_3"].conv1[0].weight.shape == (32, 320, 3, 3)
+    assert m.decoder.blocks["x_1_3"].conv1[0].weight.shape == (64, 256, 3, 3)
+    with torch.no_grad():
+        assert ref(torch.zeros(1, 3, 64, 96)).shape == (1, 1, 64, 96)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.eval()(torch.zeros(1, 3, 64, 64))
+    assert sum(p.numel() for p in O.build("resnet50", arch="UnetPlusPlus").parameters()) == 48_985_745

@@ -280,3 +280,36 @@ def test_large_decoder_resnet50_reference_yaml(cuda_device):
     with torch.no_grad():
         y32 = ref(x)
     assert_close_to_oracle(m(x.to(cuda_device)).cpu(), y32, O.forward_bf16_emulated(ref, x))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# UnetPlusPlus (the reference's default MODEL.NAME)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("enc,size,batch", [("resnet34", (128, 128), 2), ("resnet34", (96, 160), 3), ("resnet50", (64, 64), 1),
+                                            ("resnet34", (512, 512), 4)])
+def test_unetplusplus_logits_match_oracle(enc, size, batch, cuda_device):
+    from unet_watermark_b200.unetpp import UnetPlusPlus
+    ref = O.build(enc, arch="UnetPlusPlus", seed=0, random_bn=True)
+    m = UnetPlusPlus(enc, encoder_weights=None)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    m = m.to(cuda_device).eval()
+    x = O.image_like_input(batch, size, seed=3)
+    before = _lib.load().uwm_kernel_launch_count()
+    y = m(x.to(cuda_device))
+    assert _lib.load().uwm_kernel_launch_count() - before > 50
+    # yardstick: the same oracle module run by stock torch in bf16 on the GPU
+    refg = O.build(enc, arch="UnetPlusPlus", seed=0, random_bn=True).to(cuda_device)
+    with torch.no_grad():
+        y32 = refg(x.to(cuda_device)).cpu()
+        y16 = refg.to(torch.bfloat16)(x.to(cuda_device).to(torch.bfloat16)).float().cpu()
+    assert y.shape == y32.shape and y.dtype == torch.float32
+    d, d16 = (y.cpu() - y32).abs(), (y16 - y32).abs()
+    assert d.max() <= MAX_FRAC * y32.abs().max() and d.mean() <= MEAN_FRAC * y32.std(), (d.max().item(), d.mean().item())
+    assert d.mean() <= 1.3 * d16.mean() + 1e-3, (d.mean().item(), d16.mean().item())
+    # masks and the other entry points
+    u8 = O.image_like_u8(batch, size, seed=5).to(cuda_device)
+    mask, lu = m.predict_mask(u8, 0.5, return_logits=True)
+    assert torch.equal(mask, (lu[:, 0] > 0).to(torch.uint8) * 255)
+    assert torch.equal(m.predict_mask(u8, 0.5, sigmoid=False), (lu[:, 0] > 0.5).to(torch.uint8) * 255)
+    assert (m.predict_proba(u8) - torch.sigmoid(lu)).abs().max() < 1e-5
+    assert torch.equal(m.predict_mask(u8, 0.5, return_logits=True)[1], lu)          # deterministic

@@ -63,12 +63,11 @@ def predict_command(args):
         print(f"警告: 配置文件不存在: {args.config}，使用默认配置")
     cfg.defrost()
     cfg.MODEL.NAME = args.model_name or cfg.MODEL.NAME
-    if cfg.MODEL.NAME != "Unet":
-        # No silent remapping: 'UnetPlusPlus' is the reference's default (config.py:15) and what its YAMLs set, but
-        # such a checkpoint has a different decoder (nested dense blocks) and cannot be loaded into the Unet path.
-        print(f"错误: MODEL.NAME={cfg.MODEL.NAME!r} 不受支持: the B200 mask path implements 'Unet' "
-              f"(resnet34/resnet50). A {cfg.MODEL.NAME} checkpoint cannot be loaded into it. If the checkpoint "
-              f"was trained with MODEL.NAME: Unet, pass --model-name Unet (or set it in the YAML).")
+    if cfg.MODEL.NAME not in ("Unet", "UnetPlusPlus"):
+        # No silent remapping of the architecture: a checkpoint only loads into the decoder it was trained with.
+        print(f"错误: MODEL.NAME={cfg.MODEL.NAME!r} 不受支持: the B200 mask path implements 'Unet' (static plan, CUDA "
+              f"graph) and 'UnetPlusPlus' (the reference default; operator sequence), resnet34/resnet50 encoders. "
+              f"Pass --model-name to override the config.")
         return 2
     if args.encoder:
         cfg.MODEL.ENCODER_NAME = args.encoder
@@ -128,7 +127,7 @@ def build_parser():
     p.add_argument("--mask-type", choices=["auto", "watermark", "text", "mixed"], default="auto",
                    help="auto: detect the watermark type per image like the reference's step 1 (predict.py:414-441); "
                         "a fixed type skips the detection (as predict_mask does)")
-    p.add_argument("--model-name", type=str, default=None, help="override cfg.MODEL.NAME (default: Unet)")
+    p.add_argument("--model-name", type=str, default=None, help="override cfg.MODEL.NAME (Unet | UnetPlusPlus; config default: UnetPlusPlus)")
     p.add_argument("--encoder", type=str, default=None, help="override cfg.MODEL.ENCODER_NAME")
     p.add_argument("--img-size", type=int, default=None, help="override cfg.DATA.IMG_SIZE")
     p.add_argument("--workers", type=int, default=8, help="CPU decode threads")

@@ -342,8 +342,13 @@ class _OutOfScope:
         self.name = name
 
     def __call__(self, *a, **k):
-        raise NotImplementedError(f"{self.name}: only 'Unet' is implemented by the B200 mask-inference path "
-                                  "(SURVEY.md §8, DESIGN.md 'out of scope')")
+        raise NotImplementedError(f"{self.name}: 'Unet' and 'UnetPlusPlus' are implemented by the B200 mask-inference "
+                                  "path (SURVEY.md §8, DESIGN.md 'out of scope')")
+
+
+def _unetplusplus(*a, **k):
+    from .unetpp import UnetPlusPlus          # imported lazily: unetpp builds on this module's encoder / blocks
+    return UnetPlusPlus(*a, **k)
 
 
 class SMPModelFactory:
@@ -351,7 +356,7 @@ class SMPModelFactory:
 
     SUPPORTED_MODELS = {
         "Unet": Unet,
-        "UnetPlusPlus": _OutOfScope("UnetPlusPlus"),
+        "UnetPlusPlus": _unetplusplus,
         "MAnet": _OutOfScope("MAnet"),
         "Linknet": _OutOfScope("Linknet"),
         "FPN": _OutOfScope("FPN"),
