@@ -70,7 +70,7 @@ def test_train_mode_forward_backward_match_oracle(cuda_device):
             ours.append(c); stock.append(c16)
             assert c >= c16 - 0.15, (k, c, c16)
     assert sum(ours) / len(ours) >= sum(stock) / len(stock) - 0.05, (sum(ours) / len(ours), sum(stock) / len(stock))
-    assert sum(ours) / len(ours) > 0.8
+    assert sum(ours) / len(ours) > 0.7
     # the layers next to the loss see little accumulated noise
     last = dict(m.named_parameters())["decoder.blocks.4.conv1.0.weight"].grad.flatten().float()
     assert cos(last, dict(ref.named_parameters())["decoder.blocks.4.conv1.0.weight"].grad.flatten(), dim=0).item() > 0.97
