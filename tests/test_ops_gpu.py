@@ -285,6 +285,24 @@ def test_prep_input_f32_and_u8(cuda_device):
     assert bool((d <= 2 ** -7 * xn.abs().max()).all())
 
 
+def test_prep_u8_is_bit_exact_with_the_reference_normalize(cuda_device):
+    """Every byte value in every channel: the fused normalisation equals bf16(albumentations' fp32 Normalize)."""
+    import numpy as np
+    from oracle import unet_oracle as O
+    img = np.zeros((32, 32, 3), np.uint8)
+    img[:16].reshape(-1, 3)[:256] = np.arange(256, dtype=np.uint8)[:, None]          # 256 values in all three channels
+    img[16:] = np.random.default_rng(0).integers(0, 256, (16, 32, 3), dtype=np.uint8)
+    want = O.val_transform(img, 32)                                                   # fp32 [3,32,32], no resize at 32x32
+    got = ops.prep_input(torch.from_numpy(img)[None].to(cuda_device))[0].cpu()       # [16,16,16] space-to-depth
+    for ph in range(2):
+        for pw in range(2):
+            for c in range(3):
+                g = got[:, :, (ph * 2 + pw) * 3 + c]
+                w = want[c, ph::2, pw::2].to(torch.bfloat16)
+                assert torch.equal(g, w), (ph, pw, c)
+    assert bool((got[:, :, 12:] == 0).all())
+
+
 def test_stem_as_s2d_conv(cuda_device):
     g = torch.Generator().manual_seed(4)
     xin = torch.randn(2, 3, 64, 96, generator=g).to(cuda_device)

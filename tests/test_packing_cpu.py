@@ -237,3 +237,25 @@ def test_two_launch_upcat_split_equals_the_single_conv():
             assert not rest.any()
             out[:, :, qh::2, qw::2] = acc
     assert torch.allclose(out + part, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_normalize_as_one_fma_equals_both_reference_operation_orders_in_bf16():
+    """prep_s2d_kernel normalises a byte with ONE fused multiply-add, fma(k, 1/(255 std), -mean/std) (csrc/glue.cuh).
+    For the ImageNet constants of get_val_transform (reference src/utils/dataset.py:389-395) that rounds to the same
+    bf16 as albumentations' fp32 order (k - 255 mean) * (1 / (255 std)) and as (k/255 - mean)/std, for every possible
+    input (256 values x 3 channels): checked here exhaustively, with the constants the kernel hard-codes."""
+    import numpy as np
+    na = np.array([0.017124755, 0.017507004, 0.017429195], dtype=np.float32)      # csrc/glue.cuh
+    nb = np.array([-2.117904, -2.0357141, -1.8044444], dtype=np.float32)
+    mean = np.array([0.485, 0.456, 0.406], dtype=np.float32)
+    std = np.array([0.229, 0.224, 0.225], dtype=np.float32)
+    k = np.arange(256, dtype=np.float32)
+
+    def bf16(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).view(torch.int16).numpy()
+    for c in range(3):
+        assert na[c] == np.float32(np.float32(1.0) / np.float32(255.0) / std[c]) and nb[c] == np.float32(-mean[c] / std[c])
+        fma = (k.astype(np.float64) * np.float64(na[c]) + np.float64(nb[c])).astype(np.float32)     # exact product and sum in fp64 = fma
+        alb = ((k - np.float32(mean[c] * np.float32(255))) * np.reciprocal(np.float32(std[c] * np.float32(255)))).astype(np.float32)
+        div = (((k * (np.float32(1) / np.float32(255))).astype(np.float32) - mean[c]).astype(np.float32) / std[c]).astype(np.float32)
+        assert np.array_equal(bf16(fma), bf16(alb)) and np.array_equal(bf16(fma), bf16(div))

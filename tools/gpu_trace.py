@@ -60,7 +60,7 @@ def main():
         for _ in range(3):
             run()
         torch.cuda.synchronize()
-        tr = torch.zeros(600, dtype=torch.int64, device=dev)
+        tr = torch.zeros(1024, dtype=torch.int64, device=dev)
         _lib.check(lib.uwm_debug_set_trace(tr.data_ptr()))
         run()
         torch.cuda.synchronize()
@@ -79,6 +79,9 @@ def main():
             if t[160 + 3 * i]:
                 e0, e1 = rel(t[400 + 2 * i]), rel(t[401 + 2 * i])
                 print(f"   {i:3d}: {rel(t[160 + 3 * i]):8d} {rel(t[161 + 3 * i]):8d} {rel(t[162 + 3 * i]):8d}   | {e0} {e1}")
+                if i < 20 and any(t[600 + 16 * i + k] for k in range(16)):
+                    print("        items (chunk in registers / staged): " + "  ".join(
+                        f"{rel(t[600 + 16 * i + 2 * k])}/{rel(t[601 + 16 * i + 2 * k])}" for k in range(8) if t[600 + 16 * i + 2 * k]))
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ from unet_watermark_b200 import _lib
 from unet_watermark_b200.unet_model import Unet
 dev = torch.device("cuda:0")
 lib = _lib.load()
-tr = torch.zeros(600, dtype=torch.int64, device=dev)
+tr = torch.zeros(1024, dtype=torch.int64, device=dev)
 _lib.check(lib.uwm_debug_set_trace(tr.data_ptr()))      # before the plan is instantiated: the pointer is baked in
 m = Unet("resnet34", encoder_weights=None).to(dev).eval()
 m.use_cuda_graph = False

@@ -207,7 +207,7 @@ __device__ __forceinline__ void umma_halo(uint32_t tmem_d, uint32_t a_lo, uint32
 // MMA 160+3*tile+{0 accumulator free, 1 first stage landed, 2 all MMAs issued}, epilogue 400+2*tile+{0 accumulator
 // full, 1 tile stored}
 __device__ __forceinline__ void halo_trace(const HaloKArgs& p, int slot) {
-  if (UWM_TRACE_OF(p) && blockIdx.x == 0 && slot < 600) p.trace[slot] = clock64();
+  if (UWM_TRACE_OF(p) && blockIdx.x == 0 && slot < 1000) p.trace[slot] = clock64();
 }
 
 // dbg bit 8 (with a trace buffer of >= 1024 + 4*grid slots): every CTA stamps its start and exit in nanoseconds
@@ -804,6 +804,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                                     __uint_as_float(b2.x), __uint_as_float(b2.y), __uint_as_float(b2.z), __uint_as_float(b2.w),
                                     __uint_as_float(b3.x), __uint_as_float(b3.y), __uint_as_float(b3.z), __uint_as_float(b3.w)};
               tmem_ld_wait();
+              if (warp == 2 && lane == 0 && it < 20 && cg0 == c_first * JN) halo_trace(p, 600 + 16 * it + 2 * n);       // item n: accumulator chunk in registers
               if (n + 1 < NIT) item_load(n + 1, (n + 1) & 1);
               if (valid || TMA) {
                 float f[16];
@@ -871,6 +872,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
                   *reinterpret_cast<uint4*>(obase + g * ostep + c + 8) = o1;
                 }
               }
+              if (warp == 2 && lane == 0 && it < 20 && cg0 == c_first * JN) halo_trace(p, 601 + 16 * it + 2 * n);       // item n: stored / staged
             }
           }
         };

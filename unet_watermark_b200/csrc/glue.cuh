@@ -27,18 +27,14 @@ __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ 
                                                        __nv_bfloat16* __restrict__ out, int n,
                                                        int h, int w) {
   pdl_launch_dependents();
-  // u8: 256 possible inputs per channel - the normalisation is tabulated once per block with the reference's fp32
-  // operation order ((x/255 - mean)/std, true division) and rounded to bf16 exactly as the per-element path would
-  __shared__ __nv_bfloat16 lut[3][256];
-  if (kU8) {
-    const float mean[3] = {0.485f, 0.456f, 0.406f};
-    const float stdv[3] = {0.229f, 0.224f, 0.225f};
-    for (int k = threadIdx.x; k < 768; k += blockDim.x) {
-      const int c = k >> 8;
-      lut[c][k & 255] = __float2bfloat16_rn(((float)(k & 255) * (1.0f / 255.0f) - mean[c]) / stdv[c]);
-    }
-    __syncthreads();
-  }
+  // u8: get_val_transform's Normalize as ONE fused multiply-add per byte, v = fma(k, 1/(255 std), -mean/std).  For the
+  // ImageNet constants this rounds to the same bf16 value as the reference's fp32 operation orders for every one of the
+  // 256 x 3 possible inputs - both albumentations' (k - 255 mean) * (1 / (255 std)) and (k/255 - mean)/std (checked
+  // exhaustively in tests/test_packing_cpu.py).  (An earlier version tabulated the values in shared memory: ncu
+  // showed it bound by the LSU queue - 24 conflicting 2-byte lookups per thread - at 19 us for 46 MB.)
+  const float na[3] = {0.017124755f, 0.017507004f, 0.017429195f};       // fp32(fp32(1/255) / std)
+  const float nb[3] = {-2.117904f, -2.0357141f, -1.8044444f};           // fp32(-mean / std)
+  auto norm = [&](uint32_t byte, int c) { return fmaf(__uint2float_rn(byte), na[c], nb[c]); };
   pdl_wait();
   const int h2 = h >> 1, w2 = w >> 1;
   if (kU8 && (w & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0) {
@@ -51,11 +47,7 @@ __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ 
       const int jj = (int)(idx % w4);
       const int i = (int)((idx / w4) % h2);
       const int b = (int)(idx / ((long long)w4 * h2));
-      uint16_t v[2][16];                         // [output pixel][channel (ph*2+pw)*3 + c], bf16 bits
-#pragma unroll
-      for (int o = 0; o < 2; ++o)
-#pragma unroll
-        for (int k = 12; k < 16; ++k) v[o][k] = 0;
+      float v[2][12];                            // [output pixel][channel (ph*2+pw)*3 + c]
 #pragma unroll
       for (int ph = 0; ph < 2; ++ph) {
         const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (((long long)b * h + (2 * i + ph)) * w + 4 * jj) * 3);
@@ -64,16 +56,16 @@ __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ 
         for (int e = 0; e < 12; ++e) {           // byte e = pixel e/3 (0..3), channel e%3
           const uint32_t byte = (q[e >> 2] >> (8 * (e & 3))) & 0xffu;
           const int px = e / 3, c = e - 3 * px;
-          v[px >> 1][(ph * 2 + (px & 1)) * 3 + c] = __bfloat16_as_ushort(lut[c][byte]);
+          v[px >> 1][(ph * 2 + (px & 1)) * 3 + c] = norm(byte, c);
         }
       }
       uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * h2 + i) * w2 + 2 * jj) * 16);
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         uint4 o0, o1;
-        o0.x = v[o][0] | ((uint32_t)v[o][1] << 16);   o0.y = v[o][2] | ((uint32_t)v[o][3] << 16);
-        o0.z = v[o][4] | ((uint32_t)v[o][5] << 16);   o0.w = v[o][6] | ((uint32_t)v[o][7] << 16);
-        o1.x = v[o][8] | ((uint32_t)v[o][9] << 16);   o1.y = v[o][10] | ((uint32_t)v[o][11] << 16);
+        o0.x = pack2(v[o][0], v[o][1]);   o0.y = pack2(v[o][2], v[o][3]);
+        o0.z = pack2(v[o][4], v[o][5]);   o0.w = pack2(v[o][6], v[o][7]);
+        o1.x = pack2(v[o][8], v[o][9]);   o1.y = pack2(v[o][10], v[o][11]);
         o1.z = 0; o1.w = 0;
         dst[2 * o] = o0;
         dst[2 * o + 1] = o1;
@@ -99,7 +91,7 @@ __global__ void __launch_bounds__(256) prep_s2d_kernel(const void* __restrict__ 
 #pragma unroll
         for (int pw = 0; pw < 2; ++pw)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = __bfloat162float(lut[c][r[pw * 3 + c]]);
+          for (int c = 0; c < 3; ++c) v[(ph * 2 + pw) * 3 + c] = norm(r[pw * 3 + c], c);
       }
     } else {
       const float* src = static_cast<const float*>(in);
@@ -138,7 +130,8 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 // MaxPool2d(kernel 3, stride 2, padding 1), NHWC bf16.  Padding is -inf (PyTorch semantics):
 // out-of-range taps are skipped.  One thread per (output pixel, 8-channel group).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPoolRows = 8;     // output rows per thread: input row 2i+1 is shared by outputs i and i+1, kept in registers
+constexpr int kPoolRows = 8;     // default output rows per thread: input row 2i+1 is shared by outputs i and i+1, kept in registers
+template <int ROWS>
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x,
                                                            __nv_bfloat16* __restrict__ y, int n,
                                                            int h, int w, int c, long long x_pitch,
@@ -146,7 +139,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
   pdl_launch_dependents();
   pdl_wait();
   const int ho = h >> 1, wo = w >> 1, cg = c >> 3;
-  const int strips = (ho + kPoolRows - 1) / kPoolRows;
+  const int strips = (ho + ROWS - 1) / ROWS;
   const long long total = (long long)n * strips * wo * cg;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -155,7 +148,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
     const int g = (int)(idx % cg);
     long long t = idx / cg;
     const int j = (int)(t % wo); t /= wo;
-    const int i0 = (int)(t % strips) * kPoolRows;
+    const int i0 = (int)(t % strips) * ROWS;
     const int b = (int)(t / strips);
     const __nv_bfloat16* img = x + (long long)b * h * w * x_pitch + g * 8;
     auto row_max = [&](int ih) {           // max over columns 2j-1 .. 2j+1 of input row ih (ih in range)
@@ -168,7 +161,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
     bool have_prev = i0 > 0;
     if (have_prev) prev = row_max(2 * i0 - 1);
 #pragma unroll 2
-    for (int i = i0; i < min(i0 + kPoolRows, ho); ++i) {
+    for (int i = i0; i < min(i0 + ROWS, ho); ++i) {
       const uint4 a = row_max(2 * i);
       const uint4 bb = row_max(2 * i + 1);                // 2i+1 < h: h even
       uint4 m = hmax8(a, bb);

@@ -1196,9 +1196,15 @@ extern "C" int uwm_head_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int 
 static int launch_maxpool(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
                           cudaStream_t st) {
   if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
-  const long long items = (long long)n * ((h / 2 + kPoolRows - 1) / kPoolRows) * (w / 2) * (c / 8);
-  launch_pdl(maxpool3x3s2_kernel, stream_grid(items, 256), 256, 0, st, static_cast<const __nv_bfloat16*>(x),
-             static_cast<__nv_bfloat16*>(y), n, h, w, c, xp, yp);
+  // output rows per thread (one thread walks a column strip and keeps the shared input row in registers): fewer rows =
+  // more threads in flight for this latency-bound stream (ncu r02: 33 % occupancy, long-scoreboard stalls at 8 rows)
+  static const int rows = []{ const char* e = getenv("UWM_POOL_ROWS"); int v = e ? atoi(e) : 4; return (v == 2 || v == 4 || v == 8) ? v : 4; }();
+  const long long items = (long long)n * ((h / 2 + rows - 1) / rows) * (w / 2) * (c / 8);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+  if (rows == 2) launch_pdl(maxpool3x3s2_kernel<2>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp);
+  else if (rows == 4) launch_pdl(maxpool3x3s2_kernel<4>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp);
+  else launch_pdl(maxpool3x3s2_kernel<8>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp);
   return post_launch("maxpool3x3s2_kernel", st);
 }
 static int launch_upsample(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
