@@ -133,6 +133,7 @@ struct alignas(64) HaloLayerRef {
   int res_layer;                            // chain layer whose output is this layer's residual, -1: produced before the chain
   int pad_[11];
 };
+static_assert(sizeof(HaloLayerRef) % 64 == 0, "HaloLayerRef must stay a multiple of 64 bytes (tensor maps are 64-byte aligned)");
 struct HaloChain {
   HaloLayerRef layer[kMaxChainLayers];
   int n_layers;
@@ -319,7 +320,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 10));
   // folded-BN bias of every output channel, staged once: the epilogue re-reads it per 16-column chunk, and the
   // trace showed that re-read missing L1 (an L2 round trip of 500-800 cycles in front of the first FADD)
-  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 20));
+  // CHAIN work queue: items are handed out by a global atomic counter (the weight producer grabs, the other roles
+  // follow through this 4-deep FIFO) - see q_get below
+  auto qfull_bar = [&](int i) { return bar_base + 8u * (4 * kHaloMaxStages + 20 + i); };
+  auto qempty_bar = [&](int i) { return bar_base + 8u * (4 * kHaloMaxStages + 24 + i); };
+  volatile int* s_items = reinterpret_cast<volatile int*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 28));
+  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (4 * kHaloMaxStages + 36));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -332,6 +338,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
     mbar_init(bres_bar, 1);
+    if (CHAIN) for (int i = 0; i < 4; ++i) { mbar_init(qfull_bar(i), 1); mbar_init(qempty_bar(i), 10); }   // consumers: weight producer, MMA, 8 epilogue warps
     fence_mbar_init();
     tma_prefetch_desc(&tm_wgt);
     if (SPX == 1) { tma_prefetch_desc(&tm_out); tma_prefetch_desc(&tm_res); }
@@ -364,8 +371,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   const int n_layers = CHAIN ? chain->n_layers : 1;
   const int t_end = CHAIN ? n_layers * p.total_tiles : (CG2 ? (p.total_tiles >> 1) : p.total_tiles);
   const int t_step = CG2 ? (G >> 1) : G;
-  // CHAIN: work item tl = layer * total_tiles + tile
+  // CHAIN: work item tl = layer * total_tiles + tile.  Items are not assigned statically: a global counter hands them
+  // out in order (the activation loader grabs, about one item ahead of the MMAs; the weight producer, the MMA thread
+  // and the epilogue warps read the same sequence from a 4-deep shared-memory FIFO).  With static striding every layer boundary
+  // falls differently against the rounds of 148 CTAs, a quarter of the CTAs always depend on the round just
+  // before theirs and throttle everyone (measured); with the counter every item's producers are the same number
+  // of grabs back, whoever runs them.
   auto layer_of = [&](int tl) { return CHAIN ? fast_div(tl, p.div_total) : 0; };
+  auto q_get = [&](int k) -> int {           // k-th item of this CTA, -1 after the last (called by ONE thread per consumer)
+    mbar_wait(qfull_bar(k & 3), (uint32_t)(k >> 2) & 1u);
+    const int v = s_items[k & 3];
+    mbar_arrive(qempty_bar(k & 3));
+    return v;
+  };
   auto tile_of = [&](int tl) {
     if (CHAIN) return tl - fast_div(tl, p.div_total) * p.total_tiles;
     if (!CG2) return tl;
@@ -394,7 +412,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     } else {
       const bool leader = elect_one();
       int s = 0; uint32_t ph = 0;
-      for (int tl = t_first; tl < t_end; tl += t_step) {
+      int qk = 0;
+      for (int tl = t_first; CHAIN || tl < t_end; tl += t_step) {
+        if (CHAIN) {
+          int item = 0;
+          if (leader) item = q_get(qk);
+          ++qk;
+          item = __shfl_sync(0xffffffffu, item, __ffs(__ballot_sync(0xffffffffu, leader)) - 1);
+          if (item < 0) break;
+          tl = item;
+        }
         const int tile = tile_of(tl);
         const int ncol = (tile - fast_div(tile, p.div_ntiles) * p.n_tiles) * p.block_n;
         if (SPXP) {
@@ -493,7 +520,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       int sa = 0; uint32_t pha = 0;
       int sb = 0; uint32_t phb = 0;
       int it = 0;
-      for (int tl = t_first; tl < t_end; tl += t_step, ++it) {
+      for (int tl = t_first; CHAIN || tl < t_end; tl += t_step, ++it) {
+      if (CHAIN) { tl = q_get(it); if (tl < 0) break; }
       const int tile = (SPX == 3) ? tile_of(tl) : 0;
         const int acc = it & nacc_mask;
         const uint32_t tmem_acc = tmem_base + (uint32_t)acc * (TG * bn);
@@ -662,7 +690,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     uint32_t res_cnt = 0;                      // residual boxes consumed by this warp (barrier parity)
     pdl_wait();                              // residual reads / output writes depend on the previous kernel
     int it = 0;
-    for (int tl = t_first; tl < t_end; tl += t_step, ++it) {
+    for (int tl = t_first; CHAIN || tl < t_end; tl += t_step, ++it) {
+      if (CHAIN) {
+        int item = 0;
+        if (lane == 0) item = q_get(it);
+        tl = __shfl_sync(0xffffffffu, item, 0);
+        if (tl < 0) break;
+      }
       const int tile = tile_of(tl);
       const int layer = layer_of(tl);
       // per-layer epilogue parameters of a chain: output / residual maps, bias row, ReLU, residual flag
@@ -911,7 +945,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     if (A_TMA) {
       // one thread, one TMA box per stage; out-of-image coordinates are zero-filled (= conv padding)
       if (lt == 0) {
-        for (int tl = t_first; tl < t_end; tl += t_step) {
+        int lk = 0;
+        for (int tl = t_first; CHAIN || tl < t_end; tl += t_step) {
+        if (CHAIN) {
+          // grab the next work item (right after the previous item's loads were issued, i.e. about one item ahead of
+          // the MMAs) and publish it to the weight producer, the MMA thread and the epilogue warps
+          mbar_wait(qempty_bar(lk & 3), ((uint32_t)(lk >> 2) & 1u) ^ 1u);
+          tl = atomicAdd(chain->dep + n_layers * p.n_img + 1, 1);
+          if (tl >= t_end) tl = -1;
+          s_items[lk & 3] = tl;
+          mbar_arrive(qfull_bar(lk & 3));
+          ++lk;
+          if (tl < 0) break;
+        }
         const int tile = tile_of(tl);
           const HaloTile t = halo_decode<TG>(p, tile);
           const int hbase = t.h0 + p.dh_min, wbase = t.w0 + p.dw_min;
@@ -1016,7 +1062,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     __threadfence();
     if (atomicAdd(ticket, 1) == G - 1) {
       for (int i = 0; i < n_layers * p.n_img; ++i) chain->dep[i] = 0;
-      *ticket = 0;
+      ticket[0] = 0;
+      ticket[1] = 0;                           // the work-item counter
       __threadfence();
     }
   }

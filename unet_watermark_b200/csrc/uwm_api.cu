@@ -1198,7 +1198,7 @@ static int launch_maxpool(const void* x, int n, int h, int w, int c, long long x
   if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
   // output rows per thread (one thread walks a column strip and keeps the shared input row in registers): fewer rows =
   // more threads in flight for this latency-bound stream (ncu r02: 33 % occupancy, long-scoreboard stalls at 8 rows)
-  static const int rows = []{ const char* e = getenv("UWM_POOL_ROWS"); int v = e ? atoi(e) : 4; return (v == 2 || v == 4 || v == 8) ? v : 4; }();
+  static const int rows = []{ const char* e = getenv("UWM_POOL_ROWS"); int v = e ? atoi(e) : 8; return (v == 2 || v == 4 || v == 8) ? v : 8; }();   // measured r02: 2 / 4 / 8 within noise
   const long long items = (long long)n * ((h / 2 + rows - 1) / rows) * (w / 2) * (c / 8);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
@@ -1445,10 +1445,12 @@ static int build_plan(uwm_model* m) {
   static const bool spx_on = []{ const char* e = getenv("UWM_SPX"); return !(e && e[0] == '0'); }();
   static const bool split_on = []{ const char* e = getenv("UWM_SPLIT_UPCAT"); return !(e && e[0] == '0'); }();
   // Multi-layer chain launches are OPT-IN (UWM_CHAIN=1).  Measured r02 (B200, B = 16, 512x512): bit-identical results; the
-  // layer2 chain (8 convs, 256 tiles each) 137 us as one launch against 8 x ~17 us under programmatic dependent launch,
-  // the layer3 chain (12 convs, 128 tiles each on 148 SMs: every item depends on the round just before it) 244 us
-  // against 12 x ~17.5 us - the just-in-time per-image dependencies cost what fill / drain / launch gaps cost the
-  // single launches, so the step does not get faster (1.049 vs 1.054 ms with the layer2 chain only, 1.085 ms with both).
+  // layer2 chain (8 convs, 256 tiles each, work items handed out by an atomic counter) 131 us as one launch against
+  // 8 x ~17 us under programmatic dependent launch; the layer3 chain (12 convs, 128 tiles each on 148 SMs: every item's
+  // producers were grabbed less than one item-time earlier) 233 us against 12 x ~17.5 us.  A tile's epilogue + store +
+  // the consumer's halo load (~8 k cycles) eat the 0.73 item-times of slack a 256-tile layer leaves on 148 SMs, so the
+  // dependencies arrive just in time and the step gains under 1 % (1.032 vs 1.040 ms with the layer2 chain, 1.059 ms with
+  // both): kept as an experiment with its trace tooling (tools/gpu_chain_ab.py, tools/gpu_trace_chain.py).
   static const bool chain_on = []{ const char* e = getenv("UWM_CHAIN"); return e && e[0] == '1'; }();
   bool spx_f[5], split_f[5];
   TRef part_t[5];
@@ -1562,7 +1564,13 @@ static int build_plan(uwm_model* m) {
     // epilogue adds that partial sum and applies the ReLU.  The partial sum is stored in bf16 (one extra rounding).
     const bool split = split_f[i];
     if (split) {
-      TRef part = part_t[i];                     // the skip half ran right behind the encoder stage (see above)
+      if (part_t[i].buf < 0) {                   // skip source is not a residual-stage output (the stem feature): emit it here
+        part_t[i] = m->dense(bh, bw, dec[i]);
+        int la = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cs[i], dec[i], 3, 1, 1, /*relu=*/0, 0);
+        m->layers[la].d.pack = UWM_PACK_TAPS_SKIP_PART; m->layers[la].d.cin_skip = cs[i];
+        add_conv(m, la, skip[i], part_t[i], nullptr);
+      }
+      TRef part = part_t[i];                     // (otherwise the skip half ran right behind its encoder stage, see above)
       int lb = add_layer(m, pre + ".conv1.0", pre + ".conv1.1", cx[i], dec[i], 3, 1, 1, /*relu=*/1, /*has_res=*/1, false,
                          /*shuffle=*/true);
       m->layers[lb].d.pack = UWM_PACK_UP2X_SHUFFLE_X_PART; m->layers[lb].d.cin_skip = cs[i];
@@ -1792,7 +1800,11 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
 // Consecutive launches of one chain group that came out as the same kernel instantiation with the same geometry
 // become ONE multi-layer launch (conv_halo.cuh CHAIN).
 static int merge_chains(std::vector<Launch>* ls, std::vector<void*>* dev_allocs) {
-  static const int min_tiles = []{ const char* e = getenv("UWM_CHAIN_MIN_TILES"); return e ? atoi(e) : 0; }();
+  // layers with fewer than ~1.5 tiles per SM are not chained by default: their items depend on the items grabbed
+  // less than one item-time earlier, so every item would wait for its producers (measured: layer3, 128 tiles per layer)
+  static const int min_tiles = []{ const char* e = getenv("UWM_CHAIN_MIN_TILES"); return e ? atoi(e) : 3 * num_sms() / 2; }();
+  static const int max_len = []{ const char* e = getenv("UWM_CHAIN_MAX"); int v = e ? atoi(e) : kMaxChainLayers; return std::max(1, std::min(v, kMaxChainLayers)); }();
+  static const int min_len = []{ const char* e = getenv("UWM_CHAIN_MIN"); return e ? atoi(e) : 2; }();
   auto chainable = [](const Launch& L) {
     const ConvLaunch& c = L.conv;
     return L.type == OP_CONV && L.chain_group > 0 && c.hargs.total_tiles >= min_tiles && c.halo && !c.spx && !c.s2d && !c.cg2 && !c.resident && c.a_tma &&
@@ -1811,11 +1823,11 @@ static int merge_chains(std::vector<Launch>* ls, std::vector<void*>* dev_allocs)
   while (i < ls->size()) {
     size_t j = i + 1;
     if (chainable((*ls)[i]))
-      while (j < ls->size() && j - i < (size_t)kMaxChainLayers && (*ls)[j].chain_group == (*ls)[i].chain_group &&
+      while (j < ls->size() && j - i < (size_t)max_len && (*ls)[j].chain_group == (*ls)[i].chain_group &&
              chainable((*ls)[j]) && same_shape((*ls)[i].conv, (*ls)[j].conv)) ++j;
     const int n = (int)(j - i);
     const size_t smem = (*ls)[i].conv.smem + (size_t)(n - 1) * (*ls)[i].conv.hargs.cout * 4;   // every layer's bias is staged
-    if (n < 2 || smem > 225u * 1024u) {
+    if (n < min_len || !chainable((*ls)[i]) || smem > 225u * 1024u) {
       for (size_t k = i; k < j; ++k) out.push_back((*ls)[k]);
       i = j;
       continue;
@@ -1839,7 +1851,7 @@ static int merge_chains(std::vector<Launch>* ls, std::vector<void*>* dev_allocs)
     hc.n_layers = n;
     hc.dep_target = a.tiles_w * a.tiles_h * a.n_tiles * 8;          // tiles of one image x 8 epilogue warps
     int* d_dep = nullptr;
-    const size_t dep_bytes = ((size_t)n * a.n_img + 1) * sizeof(int);
+    const size_t dep_bytes = ((size_t)n * a.n_img + 2) * sizeof(int);     // counters, CTA ticket, work-item counter
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_dep), dep_bytes));
     dev_allocs->push_back(d_dep);
     CUDA_TRY(cudaMemset(d_dep, 0, dep_bytes));
