@@ -1,0 +1,106 @@
+"""Assemble profiles/r02_summary.md from the raw round-2 measurement files already copied into profiles/."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(R, "profiles")
+
+
+def bench(c):
+    return json.loads(open(os.path.join(P, f"r02_bench_config{c}.json")).read().strip().splitlines()[-1])
+
+
+def glue(n):
+    rows = list(csv.reader(open(os.path.join(P, f"r02_glue_{n}_raw.csv"))))
+    h, u, r = rows[0], rows[1], rows[2]
+    g = lambda k: r[h.index(k)]  # noqa: E731
+    return dict(us=float(g("gpu__time_duration.sum")), rd=g("dram__bytes_read.sum") + " " + u[h.index("dram__bytes_read.sum")],
+                wr=g("dram__bytes_write.sum") + " " + u[h.index("dram__bytes_write.sum")],
+                dram_r=g("dram__bytes_read.sum.pct_of_peak_sustained_elapsed"), dram_w=g("dram__bytes_write.sum.pct_of_peak_sustained_elapsed"),
+                occ=g("sm__warps_active.avg.pct_of_peak_sustained_active"), l2=g("lts__throughput.avg.pct_of_peak_sustained_elapsed"))
+
+
+def main():
+    b = {c: bench(c) for c in (2, 3, 4, 5)}
+    rows = list(csv.reader(open(os.path.join(P, "r02_launches.csv"))))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, data = r, rows[i + 1:]
+            break
+    kn, mv, mn, mu = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Name", "Metric Unit"))
+    agg, tot = collections.OrderedDict(), 0.0
+    for r in data:
+        if len(r) <= mv or r[mn] != "gpu__time_duration.sum":
+            continue
+        t = float(r[mv].replace(",", ""))
+        t = t / 1000.0 if r[mu] in ("ns", "nsecond") else t
+        k = r[kn].replace("void ", "").split("(")[0]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1; a[1] += t; tot += t
+    conv = sum(t for k, (n, t) in agg.items() if k.startswith("conv_"))
+    names = [ln.split()[0] for ln in open(os.path.join(P, "r02_layer_times.txt")).read().splitlines()[1:-1]
+             if not ln.startswith(("prep", "encoder.maxpool"))]
+    open("/tmp/conv_names.txt", "w").write("\n".join(names) + "\n")
+    table = subprocess.run([sys.executable, os.path.join(R, "tools", "ncu_raw_table.py"), os.path.join(P, "r02_convs_raw.csv"),
+                            "--names", "/tmp/conv_names.txt"], capture_output=True, text=True).stdout
+    gp, gm = glue("prep"), glue("pool")
+    d = b[2]
+    o = []
+    w = o.append
+    w("# Round 2, end of round (final build) - measurements on B200\n")
+    w("All numbers from `gpurun` calls on fresh B200 boxes with the round-2 final build; raw files alongside:")
+    w("`r02_bench_config{2,3,4,5}.json` (bench.py lines), `r02_bench_reference_arm.json`, `r02_launches.csv` (ncu launch list),")
+    w("`r02_convs_raw.csv` (ncu --set full raw page of the 49 conv launches), `r02_glue_{prep,pool}_raw.csv`, `r02_layer_times.txt`,")
+    w("`r02_cli_*.json` (CLI throughput), `r02_trace_*.txt` (in-kernel timelines), `r02_scale8_*.json` (8 GPUs), `sass_digest.txt`.\n")
+    w("## bench.py, one B200 (`python bench.py [--config N] --steps 20 --warmup 5`)\n")
+    w("| config | workload | images/s (`value`) | ms/step | whole-step fraction of the bf16 burst peak | `roofline.frac` (conv kernels) | `e2e` images/s | sustained >= 3 s: images/s, fraction of burst / sustained peak, SM MHz | same-GPU cuDNN control | CPU port (16 threads) |")
+    w("|---|---|---|---|---|---|---|---|---|---|")
+    for c in (2, 3, 4):
+        x = b[c]; s = x["sustained"]
+        w(f"| {c} | {x['config']['encoder']} {x['config']['image'][0]}x{x['config']['image'][1]} B={x['config']['batch_per_gpu']} | {x['value']:.0f} | "
+          f"{x['ms_per_step']:.3f} | {x['frac_of_bf16_peak']:.3f} | {x['roofline']['frac']:.3f} | {x['e2e']['value']:.0f} | {s['value']:.0f}, "
+          f"{s['frac_of_bf16_burst_peak']:.3f} / {s['frac_of_bf16_sustained_peak']:.3f}, {s['clocks']['sm_mhz']} ({', '.join(s['clocks']['reasons']) or 'no reason'}) | "
+          f"{x['gpu_control']['value']:.0f} ({x['value'] / x['gpu_control']['value']:.1f}x) | {x['cpu_baseline']['value']:.1f} |")
+    x = b[5]
+    w(f"| 5 | resnet34 512x512 B=16 training step (Dice+BCE, Adam) | {x['value']:.0f} | {x['ms_per_step']:.2f} | {x['frac_of_bf16_peak']:.3f} (3x forward FLOPs) | - | "
+      f"{x['e2e']['value']:.0f} | - | - | {x['cpu_baseline']['value']:.1f} |")
+    w("")
+    st = d["e2e"]["stage_ms"]
+    w(f"Config 2 `e2e` stages (CUDA events per stream, mean per step): H2D {st['h2d']:.3f} ms, compute {st['compute']:.3f} ms, D2H {st['d2h']:.3f} ms - the copies hide under the kernels.")
+    w(f"Clocks during the timed 20 steps: {d['clocks']}.  The sustained leg (same kernels, 3 s) runs at {d['sustained']['clocks']['sm_mhz']} MHz under `sw_power_cap`: "
+      "the burst line is what a 22 ms burst does, the sustained line what a folder of images gets.")
+    w("Round 1 (driver, BENCH_r01): 14 688 images/s, 1.089 ms/step, 0.559 whole step / 0.586 conv kernels.  This round on the default path: the prep normalisation as one FMA per "
+      "byte instead of a shared-memory LUT (23 -> 19 us); the conv kernels are unchanged (DESIGN.md §5 lists what was tried and measured).\n")
+    w("## ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 800 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-control --no-sustained`; `r02_launches.csv`)\n")
+    w("First 800 launches of the bench process (cold-cache, serialised: compare shares).  Template arguments: `conv_halo_kernel<KC, KH, KW, TG, RESIDENT, A_TMA, SPX, S2D, CG2, CHAIN>`.\n")
+    w("| kernel | launches | total us | share |")
+    w("|---|---|---|---|")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        w(f"| {k} | {n} | {t:.1f} | {100 * t / tot:.1f}% |")
+    w(f"\nConv kernels: {100 * conv / tot:.1f} % of the kernel time here; bench.py's live CUDA-event split (`roofline.conv_share`): {100 * d['roofline']['conv_share']:.1f} %.\n")
+    w("## `ncu --set full --clock-control none`, the 49 conv launches of one eager forward (`r02_convs_raw.csv`; table by tools/ncu_raw_table.py)\n")
+    w(table)
+    w("`profiles/roofline_traffic.json` (what bench.py reports as `roofline.traffic`, flagged `traffic_static`) holds this capture's DRAM total.\n")
+    w("## Glue kernels, `ncu --set full` (north star: achieved HBM GB/s against the B200 peak; `r02_glue_*_raw.csv`)\n")
+    w("| kernel | us | DRAM read | DRAM written | DRAM read / write % of peak | L2 throughput % | warps active % | reading |")
+    w("|---|---|---|---|---|---|---|---|")
+    w(f"| `prep_s2d_kernel<u8>` (LUT version, captured before this round's change) | {gp['us']:.1f} | {gp['rd']} | {gp['wr']} | {float(gp['dram_r']):.1f} / {float(gp['dram_w']):.1f} | {float(gp['l2']):.1f} | {float(gp['occ']):.1f} | "
+      "not DRAM-bound (its 33.5 MB output stays in L2): the stall reason was `mio_throttle` - 24 bank-conflicting 2-byte LUT lookups per thread - so the LUT became one FMA per byte |")
+    w(f"| `maxpool3x3s2_kernel` | {gm['us']:.1f} | {gm['rd']} | {gm['wr']} | {float(gm['dram_r']):.1f} / {float(gm['dram_w']):.1f} | {float(gm['l2']):.1f} | {float(gm['occ']):.1f} | "
+      "a latency-bound stream (long-scoreboard stalls, 33 % occupancy at 68 registers): 134 MB read at 3.8 TB/s = 0.58 of the 6.52 TB/s copy peak; 2 / 4 / 8 output rows per thread measure the same |")
+    w("\nEvent-timed in the eager pass (`r02_layer_times.txt`, algorithmic bytes): prep 19.8 us (46 MB, output L2-resident), max-pool 43.1 us (168 MB -> 3.9 TB/s = 0.60 of peak), "
+      "head 37.1 us (138 MB -> 3.7 TB/s = 0.57), decoder.4.conv2 54.5 us (268 MB -> 4.9 TB/s = 0.76).\n")
+    for extra in ("r02_extra.md",):
+        pth = os.path.join(P, extra)
+        if os.path.exists(pth):
+            w(open(pth).read())
+    open(os.path.join(P, "r02_summary.md"), "w").write("\n".join(o))
+    print("wrote profiles/r02_summary.md", len("\n".join(o)))
+
+
+if __name__ == "__main__":
+    main()
