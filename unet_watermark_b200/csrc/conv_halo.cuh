@@ -110,6 +110,7 @@ struct HaloKArgs {
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
   int shuffle;                              // > 0: sub-pixel mode, real cout; GEMM column n = parity*shuffle + co is stored to
                                             // pixel (2h + parity/2, 2w + parity%2), channel co of the 2x larger output (pixel shuffle)
+  int reverse;                              // walk the tiles from the last to the first (serpentine order across launches, see build_plan)
   long long* trace;                         // bench-only: CTA 0 writes clock64() stamps of its pipeline events (tools/gpu_trace.py)
   int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
 };
@@ -223,6 +224,20 @@ __device__ __forceinline__ void halo_trace_cta(const HaloKArgs& p, int which) {
   }
 }
 
+// S2D: parity plane k = (ph,pw) of a space-to-depth tensor meets tap (r,c) of the 3x3 block neighbourhood only for
+// r in {1-ph, 2-ph} and c in {1-pw, 2-pw}: 16 of the 36 (tap, plane) pairs.  s2d_pair = position of a meeting pair in
+// (tap, plane) order = index of its [N x 16] weight block in shared memory.
+__host__ __device__ constexpr bool s2d_meets(int tap, int k) {
+  return (tap / 3 == 1 - (k >> 1) || tap / 3 == 2 - (k >> 1)) && (tap % 3 == 1 - (k & 1) || tap % 3 == 2 - (k & 1));
+}
+__host__ __device__ constexpr int s2d_pair(int tap, int k) {
+  // meeting pairs per tap: 1 2 1 / 2 4 2 / 1 2 1
+  int j = tap == 0 ? 0 : tap == 1 ? 1 : tap == 2 ? 3 : tap == 3 ? 4 : tap == 4 ? 6 : tap == 5 ? 10 : tap == 6 ? 12 : tap == 7 ? 13 : 15;
+  for (int kk = 0; kk < k; ++kk) if (s2d_meets(tap, kk)) ++j;
+  return j;
+}
+static_assert(s2d_pair(8, 0) == 15 && s2d_pair(4, 3) == 9 && s2d_pair(5, 2) == 11, "S2D weight block order");
+
 struct HaloTile { int n_tile, w0, h0, img; };
 template <int TG>
 __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
@@ -303,7 +318,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 
   const int nk = NT * p.chunks;
   const uint32_t b_stage_bytes = (uint32_t)p.kpb * p.b_slice_bytes;
-  const uint32_t b_bytes_total = RESIDENT ? (uint32_t)nk * p.b_slice_bytes : (uint32_t)p.b_stages * b_stage_bytes;
+  // S2D: only the 16 meeting (tap, plane) blocks of [block_n x 16] weights are kept (32-byte rows, 32B swizzle)
+  const uint32_t b_bytes_total = S2D ? ((16u * (uint32_t)p.block_n * 32u + 1023u) & ~1023u)
+                                 : RESIDENT ? (uint32_t)nk * p.b_slice_bytes : (uint32_t)p.b_stages * b_stage_bytes;
   const uint32_t b_base = smem_base;
   const uint32_t a_base = smem_base + b_bytes_total;
   const uint32_t stg_base = (a_base + (uint32_t)p.a_stages * A_STAGE_BYTES + 1023u) & ~1023u;   // epilogue staging
@@ -386,7 +403,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   };
   auto tile_of = [&](int tl) {
     if (CHAIN) return tl - fast_div(tl, p.div_total) * p.total_tiles;
-    if (!CG2) return tl;
+    if (!CG2) return p.reverse ? p.total_tiles - 1 - tl : tl;
     const int mu = fast_div(tl, p.div_ntiles);
     return (2 * mu + (int)crank) * p.n_tiles + (tl - mu * p.n_tiles);
   };
@@ -400,7 +417,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ weight TMA producer
     const uint32_t slice_tx = (uint32_t)p.block_n * KC * 2u;
-    if (RESIDENT) {
+    if (S2D) {
+      // the weights arrive in the [N][9 x 64] layout of every 3x3 conv; tm_a1 (no second source in this form) views
+      // them in [N x 16] boxes, and only the blocks a parity plane can meet are fetched
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bres_bar, 16u * (uint32_t)p.block_n * 32u);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int k = 0; k < 4; ++k)
+            if (s2d_meets(tap, k))
+              tma_load_2d(b_base + (uint32_t)s2d_pair(tap, k) * (uint32_t)p.block_n * 32u, &tm_a1, bres_bar, tap * 64 + 16 * k, 0);
+      }
+      __syncwarp();
+    } else if (RESIDENT) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bres_bar, (uint32_t)nk * slice_tx);
         for (int ch = 0; ch < p.chunks; ++ch)
@@ -556,11 +584,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
               for (int g = 0; g < TG; ++g) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
-                  if (S2D) {       // parity plane k = (ph,pw) meets taps {1-ph,2-ph} x {1-pw,2-pw} only (folds at compile time)
-                    const int r = R0 + tap / NC, c = C0 + tap % NC, ph = k >> 1, pw = k & 1;
-                    if (!((r == 1 - ph || r == 2 - ph) && (c == 1 - pw || c == 2 - pw))) continue;
+                  if (S2D) {       // parity plane k meets 4 of the 9 taps (folds at compile time); its weight block is pair j
+                    if (!s2d_meets(tap, k)) continue;
+                    constexpr uint32_t b_hi_s2d = ((8u * 32u) >> 4) | (1u << 14) | (kLayoutSw32 << 29);
+                    const uint32_t b_blk = b_lo0 + (uint32_t)s2d_pair(tap, k) * (bn * 2u);          // bn x 32 bytes per block
+                    if (tap == 0 && k == 3)
+                      umma_halo<false, CG2>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
+                                            b_blk, b_hi_s2d, idesc, (uint32_t)ch);
+                    else
+                      umma_halo<true, CG2>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
+                                           b_blk, b_hi_s2d, idesc, 1u);
+                    continue;
                   }
-                  if (tap == 0 && k == (S2D ? 3 : 0))
+                  if (tap == 0 && k == 0)
                     umma_halo<false, CG2>(tmem_acc + g * bn, a_st + (shift + 8u * g) * a_px_units + k * a_k_units, a_hi,
                                           b_lo + 2u * k, b_hi, idesc, (uint32_t)ch);
                   else

@@ -135,14 +135,18 @@ template <int ROWS>
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x,
                                                            __nv_bfloat16* __restrict__ y, int n,
                                                            int h, int w, int c, long long x_pitch,
-                                                           long long y_pitch) {
+                                                           long long y_pitch, int reverse) {
   pdl_launch_dependents();
   pdl_wait();
   const int ho = h >> 1, wo = w >> 1, cg = c >> 3;
   const int strips = (ho + ROWS - 1) / ROWS;
   const long long total = (long long)n * strips * wo * cg;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const long long n32 = (total + 31) >> 5;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n32 * 32;
+       it += (long long)gridDim.x * blockDim.x) {
+    // reverse: the 32-item groups (one warp each) are walked back to front, lanes keep their order
+    const long long idx = reverse ? ((n32 - 1 - (it >> 5)) << 5 | (it & 31)) : it;
+    if (idx >= total) continue;
     // a warp = 4 adjacent output columns x 8 channel groups: every load instruction covers whole 128-byte lines, and
     // the column 2j+1 shared with the neighbouring output is an L1 hit
     const int g = (int)(idx % cg);

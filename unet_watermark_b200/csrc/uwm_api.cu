@@ -561,7 +561,9 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const size_t a_stage = a_stage_of(tg);
       const size_t b_slice = ((size_t)bn * kc * 2 + 1023) & ~(size_t)1023;
       const int n_tiles = s.cout_pad / bn;
-      const bool resident = (n_tiles == 1) && !par_tiles && ((size_t)nk * b_slice + 2 * a_stage <= kBudget);
+      // S2D kernels keep the 16 [bn x 16] weight blocks a parity plane can meet instead of 9 x 4 (conv_halo.cuh)
+      const size_t res_bytes = s.s2d ? (((size_t)16 * bn * 32 + 1023) & ~(size_t)1023) : (size_t)nk * b_slice;
+      const bool resident = (n_tiles == 1) && !par_tiles && (res_bytes + 2 * a_stage <= kBudget);
       if (!resident && (tg > 2 || 2 * b_slice + 2 * a_stage > kBudget)) break;   // streamed kernels: TG 1, 2
       if (s.s2d && (!resident || tg > 4 || !a_tma)) break;         // S2D: resident weights, TG 1, 2, 4, TMA-fed
       if (s.s2d && s.head && tg > 2) break;                        // head: 79 KB stages at TG 4 leave a 2-deep ring (measured slower)
@@ -574,7 +576,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
       const double issue = 6.0 * (60.0 * a.chunks + 12.0 * nk + 3.0 * mmas);
       const double a_bytes = (double)halo_npix(tg, kh, kw) * cin_total * 2;
       const double b_bytes = resident ? 0.0 : (double)bn * nk * kc * 2;
-      const int a_stages_fit = (int)((kBudget - (resident ? (size_t)nk * b_slice : 2 * b_slice)) / a_stage);
+      const int a_stages_fit = (int)((kBudget - (resident ? res_bytes : 2 * b_slice)) / a_stage);
       const double shallow = a_stages_fit < 3 ? 1.08 : 1.0;        // two stages hide the load latency a little less well (measured)
       // + ~450 cycles per tile of barrier hand-offs that nothing overlaps (trace: 2220-cycle cadence on 1764 cycles of MMAs)
       const double t_sm = waves * (std::max(std::max(tensor, issue), (a_bytes + b_bytes) / 64.0) * shallow + 450.0);
@@ -619,7 +621,7 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
   unsigned grid = (unsigned)std::min(a.total_tiles, sms);
   if (cg2) grid &= ~1u;
   a.b_slice_bytes = (((uint32_t)bn >> (cg2 ? 1 : 0)) * kc * 2u + 1023u) & ~1023u;    // a pair holds half of the rows per CTA
-  const size_t resident_bytes = (size_t)nk * a.b_slice_bytes;
+  const size_t resident_bytes = s.s2d ? (((size_t)16 * bn * 32 + 1023) & ~(size_t)1023) : (size_t)nk * a.b_slice_bytes;
   if (best.resident) {
     a.kpb = 1; a.b_stages = 1;
     a.a_stages = (int)std::min<size_t>(kHaloMaxStages, (kBudget - resident_bytes) / a_stage_bytes);
@@ -714,9 +716,17 @@ static int build_halo(const ConvSpec& s, ConvLaunch* L) {
     L->tm_res = L->tm_wgt;
   }
   L->tm_a0 = L->tm_wgt; L->tm_a1 = L->tm_wgt;
+  if (s.s2d) {
+    // the same weights in [bn x 16] boxes (32-byte rows, 32B swizzle): one box per (tap, parity plane) pair that can meet
+    cuuint32_t box16[2] = {16, (cuuint32_t)bn};
+    r = enc(&L->tm_a1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(s.wgt), dims, strides, box16, est,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(UWM_ECUDA, "cuTensorMapEncodeTiled(s2d wgt) -> %d", (int)r);
+  }
   if (a_tma || s.x2) {                  // !a_tma with a skip source: only the skip source's box map is used (mix)
     for (int i = a_tma ? 0 : 1; i < 2; ++i) {
-      if (i == 1 && !s.x2) { L->tm_a1 = L->tm_a0; break; }
+      if (i == 1 && !s.x2) { if (!s.s2d) L->tm_a1 = L->tm_a0; break; }
       const void* base = i ? s.x2 : s.x;
       const long long pitch = i ? s.x2_pitch : s.x_pitch;
       const int csrc = i ? s.cin2 : s.cin;
@@ -1193,7 +1203,7 @@ extern "C" int uwm_head_s2d_nhwc_bf16(const void* d_x, int n, int h, int w, int 
   return launch_conv(L, static_cast<cudaStream_t>(stream));
 }
 
-static int launch_maxpool(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
+static int launch_maxpool(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp, int reverse,
                           cudaStream_t st) {
   if (c % 8 || h % 2 || w % 2) return fail(UWM_EINVAL, "maxpool: c%%8, h%%2, w%%2 must be 0");
   // output rows per thread (one thread walks a column strip and keeps the shared input row in registers): fewer rows =
@@ -1202,9 +1212,9 @@ static int launch_maxpool(const void* x, int n, int h, int w, int c, long long x
   const long long items = (long long)n * ((h / 2 + rows - 1) / rows) * (w / 2) * (c / 8);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
-  if (rows == 2) launch_pdl(maxpool3x3s2_kernel<2>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp);
-  else if (rows == 4) launch_pdl(maxpool3x3s2_kernel<4>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp);
-  else launch_pdl(maxpool3x3s2_kernel<8>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp);
+  if (rows == 2) launch_pdl(maxpool3x3s2_kernel<2>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp, reverse);
+  else if (rows == 4) launch_pdl(maxpool3x3s2_kernel<4>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp, reverse);
+  else launch_pdl(maxpool3x3s2_kernel<8>, stream_grid(items, 256), 256, 0, st, xb, yb, n, h, w, c, xp, yp, reverse);
   return post_launch("maxpool3x3s2_kernel", st);
 }
 static int launch_upsample(const void* x, int n, int h, int w, int c, long long xp, void* y, long long yp,
@@ -1231,7 +1241,7 @@ static int launch_prep(const void* in, int fmt, int n, int h, int w, void* y, cu
 extern "C" int uwm_maxpool3x3s2_nhwc_bf16(const void* d_x, int n, int h, int w, int c, int x_pitch,
                                           void* d_y, int y_pitch, void* stream) {
   if (!d_x || !d_y) return fail(UWM_EINVAL, "maxpool: null pointer");
-  return launch_maxpool(d_x, n, h, w, c, x_pitch, d_y, y_pitch, static_cast<cudaStream_t>(stream));
+  return launch_maxpool(d_x, n, h, w, c, x_pitch, d_y, y_pitch, 0, static_cast<cudaStream_t>(stream));
 }
 extern "C" int uwm_upsample2x_nhwc_bf16(const void* d_x, int n, int h, int w, int c, int x_pitch,
                                         void* d_y, int y_pitch, void* stream) {
@@ -1287,6 +1297,7 @@ struct Launch {          // one kernel of an instantiated plan
   int n = 0, h = 0, w = 0, c = 0;
   long long src_pitch = 0, dst_pitch = 0;
   bool side = false, join = false;
+  int reverse = 0;                         // OP_POOL: walk the tensor back to front (convs: conv.hargs.reverse)
   int chain_group = 0;
   int chain_len = 0;                       // > 1: multi-layer chain launch
   HaloChain* d_chain = nullptr;            // device copy of the chain table (owned by the plan)
@@ -1734,6 +1745,12 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
                        uint8_t* d_mask, float thr_logit, std::vector<Launch>* out, std::vector<void*>* dev_allocs) {
   out->clear();
   out->reserve(m->ops.size());
+  // Serpentine tile order (UWM_SERP, default on): a launch walks its tiles in the opposite direction of the launch that
+  // wrote its input, so it starts on the most recently written - still L2-resident - end of a tensor that is larger
+  // than L2 (stem -> max-pool, decoder block 4 -> head: 134 MB each at 16 x 512 x 512), instead of on the end that the
+  // producer's later writes have already evicted.
+  static const bool serp = []{ const char* e = getenv("UWM_SERP"); return !(e && e[0] == '0'); }();
+  std::map<const void*, int> dir_of;         // tensor base -> direction its producer walked (1 = back to front)
   for (const Op& op : m->ops) {
     Launch L;
     L.type = op.type;
@@ -1791,6 +1808,14 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
         if (rc) return rc;
         break;
       }
+    }
+    if (serp && op.type != OP_PREP) {
+      const auto it = dir_of.find(m->ptr(op.in));
+      int dir = (it == dir_of.end() ? 0 : it->second) ^ 1;
+      if (op.type == OP_POOL) L.reverse = dir;
+      else if (L.conv.halo && !L.conv.cg2 && op.chain_group == 0) L.conv.hargs.reverse = dir;
+      else dir = 0;
+      if (op.type != OP_HEAD) dir_of[m->ptr(op.out)] = dir;
     }
     out->push_back(L);
   }
@@ -1892,7 +1917,7 @@ static int run_launch(const Launch& L, cudaStream_t st) {
   PlanScope in_plan;
   switch (L.type) {
     case OP_PREP: return launch_prep(L.src, L.c, L.n, L.h, L.w, L.dst, st);
-    case OP_POOL: return launch_maxpool(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, st);
+    case OP_POOL: return launch_maxpool(L.src, L.n, L.h, L.w, L.c, L.src_pitch, L.dst, L.dst_pitch, L.reverse, st);
     case OP_CONV:
     case OP_HEAD:
       if (L.chain_len > 1) {
