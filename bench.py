@@ -492,6 +492,9 @@ def run_ours(args):
     sync_all()
     # per-stage device time of one step on its own stream (mean over the timed steps): names the exposed stage
     stage_ms = [sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for ev in stage_ev) / max(len(stage_ev), 1) for k in range(3)]
+    # interval between consecutive completed downloads in the same pass: the pipeline's steady-state step time, i.e. the
+    # timed K-step figure without its one-off fill (first upload) and drain (last download)
+    steady_ms = (stage_ev[0][5].elapsed_time(stage_ev[-1][5]) / (len(stage_ev) - 1)) if len(stage_ev) > 1 else 0.0
 
     # ---- sustained leg: >= 3 s of back-to-back graph replays (device-resident), own clock record --------
     sustained = None
@@ -511,13 +514,14 @@ def run_ours(args):
         sustained = {"steps": n_sus, "ms_total": ms_sus, "ms_per_step": ms_sus / n_sus, "clocks": samp2.stop()}
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, sustained["ms_total"] if sustained else 0.0] + stage_ms, device=dev,
+        t = torch.tensor([ms_total, ms_e2e, sustained["ms_total"] if sustained else 0.0] + stage_ms + [steady_ms], device=dev,
                          dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
         if sustained:
             sustained["ms_total"] = float(t[2]); sustained["ms_per_step"] = float(t[2]) / sustained["steps"]
         stage_ms = [float(v) for v in t[3:6]]
+        steady_ms = float(t[6])
 
     # ---- GPU control: the oracle module as stock torch bf16 channels_last (cuDNN) on the same GPU ---------
     gpu_control = None
@@ -594,6 +598,9 @@ def run_ours(args):
                                "double-buffered over H2D / compute / D2H streams",
                         "stage_ms": {"h2d": stage_ms[0], "compute": stage_ms[1], "d2h": stage_ms[2],
                                      "how": "CUDA events around each stage on its own stream, mean per step, max over ranks"},
+                        "steady_state": {"value": world * BATCH / (steady_ms * 1e-3) if steady_ms > 0 else None, "ms_per_step": steady_ms,
+                                         "how": "mean interval between consecutive completed downloads; `value` above also carries the "
+                                                "one-off pipeline fill (first upload) and drain (last download) of the K timed steps"},
                         "mask_checksum": e2e_checksum},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "mask_checksum": checksum}
         if sustained:

@@ -12,4 +12,6 @@ $CMD > $O/r02_plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clo
 CMD2="python tools/profile_run.py --passes 3"
 $CMD2 > $O/r02_plain_profile.log 2>&1 && ncu --set full --clock-control none -k regex:conv_halo_kernel -s 98 -c 49 -o $O/r02_convs -f $CMD2 > $O/r02_ncu_convs.log 2>&1
 ncu -i $O/r02_convs.ncu-rep --page raw --csv > $O/r02_convs_raw.csv 2>/dev/null; rm -f $O/r02_convs.ncu-rep
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+ncu --metrics $M --cache-control none --clock-control none --graph-profiling node -c 420 --csv --log-file $O/r02_warm_dram_final.csv $CMD > $O/r02_warm_dram_final.log 2>&1
 tail -3 $O/r02_final_pytest.log; ls -la $O | tail -15
