@@ -3,6 +3,7 @@ import collections
 import csv
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -73,8 +74,13 @@ def main():
     w(f"Config 2 `e2e` stages (CUDA events per stream, mean per step): H2D {st['h2d']:.3f} ms, compute {st['compute']:.3f} ms, D2H {st['d2h']:.3f} ms - the copies hide under the kernels.")
     w(f"Clocks during the timed 20 steps: {d['clocks']}.  The sustained leg (same kernels, 3 s) runs at {d['sustained']['clocks']['sm_mhz']} MHz under `sw_power_cap`: "
       "the burst line is what a 22 ms burst does, the sustained line what a folder of images gets.")
-    w("Round 1 (driver, BENCH_r01): 14 688 images/s, 1.089 ms/step, 0.559 whole step / 0.586 conv kernels.  This round on the default path: the prep normalisation as one FMA per "
-      "byte instead of a shared-memory LUT (23 -> 19 us); the conv kernels are unchanged (DESIGN.md §5 lists what was tried and measured).\n")
+    ss = d["e2e"].get("steady_state") or {}
+    if ss.get("value"):
+        w(f"`e2e` over the 20 timed steps carries the one-off pipeline fill (first upload) and drain (last download); the interval between completed downloads in steady state is "
+          f"{ss['ms_per_step']:.3f} ms = {ss['value']:.0f} images/s.")
+    w("Round 1 (driver, BENCH_r01): 14 688 images/s, 1.089 ms/step, 0.559 whole step / 0.586 conv kernels.  This round on the default path: serpentine tile order across launches "
+      "(-1.8 %), the space-to-depth convs keep only the 16 weight blocks a parity plane can meet and gain a third activation stage (-1.0 %, config 3 -3.9 %), the prep normalisation "
+      "as one FMA per byte instead of a shared-memory LUT (23 -> 15 us); `r02_l2_experiments.md` and DESIGN.md §5 list what else was tried and measured.\n")
     w("## ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 800 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-control --no-sustained`; `r02_launches.csv`)\n")
     w("First 800 launches of the bench process (cold-cache, serialised: compare shares).  Template arguments: `conv_halo_kernel<KC, KH, KW, TG, RESIDENT, A_TMA, SPX, S2D, CG2, CHAIN>`.\n")
     w("| kernel | launches | total us | share |")
@@ -84,7 +90,14 @@ def main():
     w(f"\nConv kernels: {100 * conv / tot:.1f} % of the kernel time here; bench.py's live CUDA-event split (`roofline.conv_share`): {100 * d['roofline']['conv_share']:.1f} %.\n")
     w("## `ncu --set full --clock-control none`, the 49 conv launches of one eager forward (`r02_convs_raw.csv`; table by tools/ncu_raw_table.py)\n")
     w(table)
-    w("`profiles/roofline_traffic.json` (what bench.py reports as `roofline.traffic`, flagged `traffic_static`) holds this capture's DRAM total.\n")
+    w("`profiles/roofline_traffic.json` (what bench.py reports as `roofline.traffic`, flagged `traffic_static`) holds this capture's DRAM total.  ncu flushes the caches before every "
+      "kernel here; a warm forward (no flushes, `r02_warm_dram_final_table.txt`) moves less - see `r02_l2_experiments.md`.\n")
+    m = re.search(r"DRAM read ([0-9.]+) MB \+ write ([0-9.]+) MB", table)
+    if m:
+        rd, wr = float(m.group(1)) * 1e6, float(m.group(2)) * 1e6
+        json.dump({"conv_dram_bytes_per_step": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                   "source": "profiles/r02_convs_raw.csv (ncu --set full, cold caches, 49 conv launches of one eager forward, round 2 final build)"},
+                  open(os.path.join(P, "roofline_traffic.json"), "w"))
     w("## Glue kernels, `ncu --set full` (north star: achieved HBM GB/s against the B200 peak; `r02_glue_*_raw.csv`)\n")
     w("| kernel | us | DRAM read | DRAM written | DRAM read / write % of peak | L2 throughput % | warps active % | reading |")
     w("|---|---|---|---|---|---|---|---|")
@@ -92,8 +105,11 @@ def main():
       "not DRAM-bound (its 33.5 MB output stays in L2): the stall reason was `mio_throttle` - 24 bank-conflicting 2-byte LUT lookups per thread - so the LUT became one FMA per byte |")
     w(f"| `maxpool3x3s2_kernel` | {gm['us']:.1f} | {gm['rd']} | {gm['wr']} | {float(gm['dram_r']):.1f} / {float(gm['dram_w']):.1f} | {float(gm['l2']):.1f} | {float(gm['occ']):.1f} | "
       "a latency-bound stream (long-scoreboard stalls, 33 % occupancy at 68 registers): 134 MB read at 3.8 TB/s = 0.58 of the 6.52 TB/s copy peak; 2 / 4 / 8 output rows per thread measure the same |")
-    w("\nEvent-timed in the eager pass (`r02_layer_times.txt`, algorithmic bytes): prep 19.8 us (46 MB, output L2-resident), max-pool 43.1 us (168 MB -> 3.9 TB/s = 0.60 of peak), "
-      "head 37.1 us (138 MB -> 3.7 TB/s = 0.57), decoder.4.conv2 54.5 us (268 MB -> 4.9 TB/s = 0.76).\n")
+    lt = {ln.split()[0]: ln.split() for ln in open(os.path.join(P, "r02_layer_times.txt")).read().splitlines()[1:-1]}
+    w("\nEvent-timed in the eager pass of the final build (`r02_layer_times.txt`: us, algorithmic GB/s against the 6521 GB/s copy peak): " +
+      ", ".join(f"{k} {lt[k][1]} us ({float(lt[k][4]):.0f} GB/s = {float(lt[k][4]) / 6521.4:.2f})" for k in
+                ("prep", "encoder.maxpool", "decoder.blocks.4.conv2.0", "segmentation_head.0") if k in lt) +
+      ".  (Both ncu rows above were captured before this round's changes to these kernels: prep LUT -> FMA, max-pool walking the tensor back to front.)\n")
     for extra in ("r02_extra.md",):
         pth = os.path.join(P, extra)
         if os.path.exists(pth):
