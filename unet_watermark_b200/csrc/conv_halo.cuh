@@ -238,6 +238,13 @@ __host__ __device__ constexpr int s2d_pair(int tap, int k) {
 }
 static_assert(s2d_pair(8, 0) == 15 && s2d_pair(4, 3) == 9 && s2d_pair(5, 2) == 11, "S2D weight block order");
 
+// max of two packed bf16 pairs (one HMNMX2)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v, uint32_t clamp) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(clamp));
+  return r;
+}
+
 struct HaloTile { int n_tile, w0, h0, img; };
 template <int TG>
 __device__ __forceinline__ HaloTile halo_decode(const HaloKArgs& p, int tile) {
@@ -699,7 +706,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
     const int row = q * 32 + lane;           // accumulator row == pixel of the 8x16 sub-tile
     const int wi = row & (kHaloTW - 1);
     const int hi = row >> 3;
-    float lo_clamp = p.relu ? 0.f : -INFINITY;
+    // ReLU on the packed bf16 pairs (8 HMNMX2 per 16 columns instead of 16 FMNMX): max(round(x), 0) == round(max(x, 0))
+    uint32_t lo_clamp2 = p.relu ? 0u : 0xff80ff80u;              // +0 | +0, or -inf | -inf = no clamp
     const uint32_t bn = (uint32_t)p.block_n;
     const int eset = (warp >= kHaloLoaderWarp0) ? 1 : 0;       // which of the two warps of this lane quarter
     constexpr int GN = (TG >= 2) ? TG / 2 : 1;                 // sub-tiles per warp: g = GSTEP*gi + g_first
@@ -739,7 +747,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       const CUtensorMap* omap = CHAIN ? &chain->layer[layer].tm_out : &tm_out;
       const CUtensorMap* rmap = CHAIN ? &chain->layer[layer].tm_res : &tm_res;
       const bool has_res = CHAIN ? (chain->layer[layer].has_res != 0) : (p.res != nullptr);
-      if (CHAIN) lo_clamp = chain->layer[layer].relu ? 0.f : -INFINITY;
+      if (CHAIN) lo_clamp2 = chain->layer[layer].relu ? 0u : 0xff80ff80u;
       const int acc = it & nacc_mask;
       const HaloTile t = halo_decode<TG>(p, tile);
       const int oh = t.h0 + hi;
@@ -897,13 +905,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
 #pragma unroll
                   for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(rr[k]); f[2 * k + 1] += bf16_hi(rr[k]); }
                 }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], lo_clamp);
                 uint4 o0, o1;
-                o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                o0.x = relu_bf16x2(pack_bf16x2(f[0], f[1]), lo_clamp2);   o0.y = relu_bf16x2(pack_bf16x2(f[2], f[3]), lo_clamp2);
+                o0.z = relu_bf16x2(pack_bf16x2(f[4], f[5]), lo_clamp2);   o0.w = relu_bf16x2(pack_bf16x2(f[6], f[7]), lo_clamp2);
+                o1.x = relu_bf16x2(pack_bf16x2(f[8], f[9]), lo_clamp2);   o1.y = relu_bf16x2(pack_bf16x2(f[10], f[11]), lo_clamp2);
+                o1.z = relu_bf16x2(pack_bf16x2(f[12], f[13]), lo_clamp2); o1.w = relu_bf16x2(pack_bf16x2(f[14], f[15]), lo_clamp2);
                 if (TMA) {
                   if (j == 0 && !RES) {  // the previous store of this warp must have read the buffer out
                     if (lane == 0) bulk_wait_read<0>();
