@@ -160,12 +160,17 @@ def _bucket_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)                                           # identical replicas
     net = nn.Sequential(nn.Linear(7, 5), nn.ReLU(), nn.Linear(5, 3), nn.ReLU(), nn.Linear(3, 1))
+    import copy
+    plain = copy.deepcopy(net)                                     # same weights, no buckets: this rank's own gradient
     buckets = GradBuckets(net.parameters(), bucket_mb=1e-4)        # ~26 floats per bucket: several buckets
     g = torch.Generator().manual_seed(100 + rank)                  # different data per rank
     x, y = torch.randn(6, 7, generator=g), torch.randn(6, 1, generator=g)
+    ((plain(x) - y) ** 2).mean().backward()
+    # (read from the un-bucketed copy: the bucketed net's all-reduces start inside backward() and run in the background,
+    # so its p.grad may already hold partial sums when backward() returns)
+    local = [p.grad.flatten().tolist() for p in plain.parameters()]    # plain lists: they cross process boundaries
     buckets.zero_grad()
     ((net(x) - y) ** 2).mean().backward()
-    local = [p.grad.flatten().tolist() for p in net.parameters()]      # plain lists: they cross process boundaries
     buckets.finish()
     avg = [p.grad.flatten().tolist() for p in net.parameters()]
     gathered = [None] * world
