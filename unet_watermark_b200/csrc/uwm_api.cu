@@ -284,9 +284,11 @@ static int build_halo_spx(const ConvSpec& s, ConvLaunch* L) {
   a.kpb = 1;
   const size_t a_stage_bytes = (((size_t)halo_npix(tg, 3, 3) * kc * 2) + 1023) & ~(size_t)1023;
   const size_t kBudget = 206u * 1024u;
-  // an activation stage lasts 4 or 9 taps (2000-4600 tensor cycles): two are enough.  The weight ring gets the rest:
-  // slices are consumed every ~512 cycles and must cover the L2 latency under load (~3000 cycles)
-  a.a_stages = 2;
+  // A skip-plane stage lasts 4 taps = ~1750 tensor cycles, less than the 2500-3400 cycles its halo box takes from HBM
+  // (the full-resolution skip tensor never sits in L2): with two stages every plane chunk waited ~800 cycles for its
+  // box (profiles/r02_trace_dec3_spx.txt), so three stages when the weight ring keeps >= 4 slices (measured, 3 runs
+  // each: config 2 -0.4 %, config 3 -1.1 %; four stages starve the weight ring, +2.7 %).
+  a.a_stages = ((kBudget - 3 * a_stage_bytes) / a.b_slice_bytes >= 4) ? 3 : 2;
   { const char* e = getenv("UWM_SPX_ASTAGES"); if (e && atoi(e) >= 2 && atoi(e) <= 4) a.a_stages = atoi(e); }
   a.b_stages = (int)std::min<size_t>(12, (kBudget - a.a_stages * a_stage_bytes) / a.b_slice_bytes);
   if (a.b_stages < 2) return fail(UWM_ESTATE, "sub-pixel upcat conv: rings do not fit shared memory");
