@@ -110,6 +110,8 @@ struct HaloKArgs {
   int ep_tma, ep_cols;                      // epilogue: TMA tensor stores of (64 ch x 8 x 4 px) boxes via smem staging (ep_cols 64), else 16
   int shuffle;                              // > 0: sub-pixel mode, real cout; GEMM column n = parity*shuffle + co is stored to
                                             // pixel (2h + parity/2, 2w + parity%2), channel co of the 2x larger output (pixel shuffle)
+  unsigned long long a_policy[2];           // A_TMA loaders: L2 eviction policy of the loads from src[0] / src[1] (0: default);
+                                            // evict_first for a source nobody reads after this launch (build_plan)
   int reverse;                              // walk the tiles from the last to the first (serpentine order across launches, see build_plan)
   long long* trace;                         // bench-only: CTA 0 writes clock64() stamps of its pipeline events (tools/gpu_trace.py)
   int dbg;                                  // bench-only bit mask: 1 skip activation loads, 2 skip MMAs, 4 skip epilogue
@@ -988,6 +990,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
       // one thread, one TMA box per stage; out-of-image coordinates are zero-filled (= conv padding)
       if (lt == 0) {
         int lk = 0;
+        const unsigned long long pol0 = p.a_policy[0] ? p.a_policy[0] : kL2EvictNormal;
+        const unsigned long long pol1 = p.a_policy[1] ? p.a_policy[1] : kL2EvictNormal;
         for (int tl = t_first; CHAIN || tl < t_end; tl += t_step) {
         if (CHAIN) {
           // grab the next work item (right after the previous item's loads were issued, i.e. about one item ahead of
@@ -1027,16 +1031,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_wgt, const __grid_consta
             } else if (!(UWM_DBG_OF(p) & 1)) {
               mbar_arrive_expect_tx(afull_bar(s), (uint32_t)NPIX * ROWB);
               if (ch < p.split_chunk)
-                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, amap, afull_bar(s), ch * KC, wbase * p.a_scale,
-                            hbase * p.a_scale, t.img);
+                tma_load_4d_hint(a_base + (uint32_t)s * A_STAGE_BYTES, amap, afull_bar(s), ch * KC, wbase * p.a_scale,
+                                 hbase * p.a_scale, t.img, pol0);
               else if (SPXP) {
                 // parity plane (ph,pw) of the full-resolution skip source: halo block b is pixel 2b + parity
                 const int e = ch - p.split_chunk, par = e / p.spx_cpp, cc = e - par * p.spx_cpp;
-                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), cc * KC, 2 * wbase + (par & 1),
-                            2 * hbase + (par >> 1), t.img);
+                tma_load_4d_hint(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), cc * KC, 2 * wbase + (par & 1),
+                                 2 * hbase + (par >> 1), t.img, pol1);
               } else
-                tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), (ch - p.split_chunk) * KC, wbase,
-                            hbase, t.img);
+                tma_load_4d_hint(a_base + (uint32_t)s * A_STAGE_BYTES, &tm_a1, afull_bar(s), (ch - p.split_chunk) * KC, wbase,
+                                 hbase, t.img, pol1);
             } else {
               mbar_arrive(afull_bar(s));
             }

@@ -121,6 +121,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 eviction policy operands of cp.async.bulk.tensor ... .L2::cache_hint (the encodings createpolicy.fractional produces
+// for fraction 1.0): evict_first = the line becomes the first eviction candidate once it has been read
+constexpr unsigned long long kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull;
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                 int c0, int c1, int c2, int c3, unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
                                             int c0, int c1, int c2, int c3, int c4) {
   asm volatile(

@@ -1753,7 +1753,17 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
   // producer's later writes have already evicted.
   static const bool serp = []{ const char* e = getenv("UWM_SERP"); return !(e && e[0] == '0'); }();
   std::map<const void*, int> dir_of;         // tensor base -> direction its producer walked (1 = back to front)
+  // evict_first loads of dead sources (UWM_L2_HINT = workspace limit in MB, default 1024, 0 = off): a conv source that
+  // nobody touches after this launch is loaded with the evict_first policy, so its lines leave L2 before the lines that
+  // are still waiting to be read.  That pays while a good part of the producer -> consumer hand-overs still hit L2
+  // (config 2: 0.6 GB of workspace, -0.6 ... -0.8 % over three runs) and costs when the forward's workspace is many
+  // times L2 and the hint only evicts the halo rows a neighbouring tile is about to re-read (config 3, 9.6 GB: +0.7 ...
+  // +1.0 %; config 4: +0.3 ... +0.6 %) - hence the limit on this batch's workspace.
+  static const double hint_mb = []{ const char* e = getenv("UWM_L2_HINT"); return e ? atof(e) : 1024.0; }();
+  const bool hint_on = hint_mb > 0 && !m->keep_all && (double)(m->arena_bytes / (size_t)m->max_batch) * batch <= hint_mb * 1e6;
+  int op_idx = -1;
   for (const Op& op : m->ops) {
+    ++op_idx;
     Launch L;
     L.type = op.type;
     L.side = op.side; L.join = op.join;
@@ -1810,6 +1820,11 @@ static int instantiate(uwm_model* m, const void* d_in, int in_fmt, int batch, fl
         if (rc) return rc;
         break;
       }
+    }
+    if (hint_on && (op.type == OP_CONV || op.type == OP_HEAD) && L.conv.halo) {
+      auto dead = [&](const TRef& t) { return t.buf >= 0 && m->bufs[t.buf].last == op_idx; };
+      if (dead(op.in)) L.conv.hargs.a_policy[0] = kL2EvictFirst;
+      if (op.has_in2 && dead(op.in2)) L.conv.hargs.a_policy[1] = kL2EvictFirst;
     }
     if (serp && op.type != OP_PREP) {
       const auto it = dir_of.find(m->ptr(op.in));
