@@ -136,3 +136,41 @@ def test_unetplusplus_reference_default_architecture_keys_and_known_answers():
     with pytest.raises(RuntimeError, match="no CPU"):
         m.eval()(torch.zeros(1, 3, 64, 64))
     assert sum(p.numel() for p in O.build("resnet50", arch="UnetPlusPlus").parameters()) == 48_985_745
+
+
+def test_sub_batch_policy(monkeypatch):
+    """Unet._sub_batch_for: explicit attribute > UWM_SUBBATCH > per-encoder pixel budget; never >= the batch."""
+    m = Unet("resnet34", encoder_weights=None)
+    monkeypatch.delenv("UWM_SUBBATCH", raising=False)
+    monkeypatch.setattr(Unet, "_SUB_BATCH_PIXELS", {})
+    assert m._sub_batch_for(16, 512, 512) == 0
+    monkeypatch.setenv("UWM_SUBBATCH", "8")
+    assert m._sub_batch_for(16, 512, 512) == 8 and m._sub_batch_for(8, 512, 512) == 0 and m._sub_batch_for(4, 512, 512) == 0
+    m.sub_batch = 4
+    assert m._sub_batch_for(16, 512, 512) == 4
+    m.sub_batch = 0
+    assert m._sub_batch_for(16, 512, 512) == 0
+    m.sub_batch = None
+    monkeypatch.delenv("UWM_SUBBATCH")
+    monkeypatch.setattr(Unet, "_SUB_BATCH_PIXELS", {"resnet34": 8 * 1024 * 1024})
+    assert m._sub_batch_for(64, 1024, 1024) == 8 and m._sub_batch_for(16, 512, 512) == 0 and m._sub_batch_for(64, 512, 512) == 32
+    assert m._sub_batch_for(4, 4096, 4096) == 1
+
+
+@pytest.mark.parametrize("shape", [(32, 16, 3), (16, 48, 1), (64, 64, 3)])
+def test_dgrad_weights_is_the_transposed_flipped_filter(shape):
+    """training.dgrad_weights: conv(gy, flipped / transposed filter) == autograd's data gradient of a 'same' conv."""
+    from unet_watermark_b200.training import dgrad_weights, native_dgrad_applies
+    cout, cin, k = shape
+    g = torch.Generator().manual_seed(cout + cin)
+    x = torch.randn(2, cin, 9, 7, generator=g, requires_grad=True)
+    w = torch.randn(cout, cin, k, k, generator=g)
+    y = F.conv2d(x, w, padding=k // 2)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    wp = dgrad_weights(w)                                          # UWM_PACK_TAPS: [Cin][k*k][Cout]
+    assert wp.shape == (cin, k * k * cout) and wp.is_contiguous()
+    gx = F.conv2d(gy, wp.view(cin, k, k, cout).permute(0, 3, 1, 2), padding=k // 2)
+    assert torch.allclose(gx, x.grad, atol=1e-4, rtol=1e-4)
+    assert native_dgrad_applies(w.shape, 1, k // 2) and not native_dgrad_applies(w.shape, 2, k // 2)
+    assert not native_dgrad_applies((cout, 3, 7, 7), 1, 3) and not native_dgrad_applies((1, 16, 3, 3), 1, 1)

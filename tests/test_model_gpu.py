@@ -313,3 +313,25 @@ def test_unetplusplus_logits_match_oracle(enc, size, batch, cuda_device):
     assert torch.equal(m.predict_mask(u8, 0.5, sigmoid=False), (lu[:, 0] > 0.5).to(torch.uint8) * 255)
     assert (m.predict_proba(u8) - torch.sigmoid(lu)).abs().max() < 1e-5
     assert torch.equal(m.predict_mask(u8, 0.5, return_logits=True)[1], lu)          # deterministic
+
+
+@pytest.mark.parametrize("enc,size,batch,sub", [("resnet34", 96, 5, 2), ("resnet50", 64, 4, 1), ("resnet34", 64, 6, 4)])
+def test_sub_batched_forward_is_bit_identical(enc, size, batch, sub, cuda_device):
+    """Engine.forward ``sub_batch``: the batch as consecutive forwards on slices of the same input / output buffers
+    (ragged last chunk included) gives the same bits as the whole batch in one plan - logits, masks and the uint8 path."""
+    _, m = make_pair(enc, cuda_device, seed=4)
+    u8 = O.image_like_u8(batch, size, seed=11).to(cuda_device)
+    x = norm_u8(u8).to(cuda_device)
+    m.sub_batch = 0
+    y0 = m(x)
+    mask0, l0 = m.predict_mask(u8, 0.5, return_logits=True)
+    m.sub_batch = sub
+    before = _lib.load().uwm_kernel_launch_count()
+    y1 = m(x)
+    chunks = -(-batch // sub)
+    assert _lib.load().uwm_kernel_launch_count() - before >= chunks * 45           # every chunk is a whole forward
+    out = torch.full((batch, size, size), 7, dtype=torch.uint8, device=cuda_device)
+    mask1, l1 = m.predict_mask(u8, 0.5, return_logits=True, out=out)
+    assert mask1.data_ptr() == out.data_ptr()
+    assert torch.equal(y0, y1) and torch.equal(l0, l1) and torch.equal(mask0, mask1)
+    assert set(mask1.unique().tolist()) <= {0, 255}

@@ -107,3 +107,66 @@ def test_train_steps_reduce_the_loss_and_eval_path_sees_new_weights(cuda_device)
     m.eval()
     assert not torch.equal(m(x), y_eval)                       # one more step changed the weights -> new plan weights
     assert any(not torch.equal(v, snapshot[k]) for k, v in m.state_dict().items() if "num_batches" not in k)
+
+
+# every data-gradient geometry of the Unet-resnet34 training step that runs on the tcgen05 kernel (gy channels = Cout of
+# the forward conv, gx channels = its Cin; the decoder conv1 gradients fan OUT to the concat's 768 / 384 / 192 / 128 channels)
+# (name, n, h, w, cin, cout, k)
+DGRAD_CASES = [
+    ("l1_64_64",        2, 32, 32,  64,  64, 3),
+    ("l2_128_128",      2, 16, 16, 128, 128, 3),
+    ("l3_256_256",      2,  8,  8, 256, 256, 3),
+    ("l4_512_512",      4,  4,  4, 512, 512, 3),
+    ("d0_conv1_768_256", 2, 8,  8, 768, 256, 3),
+    ("d1_conv1_384_128", 1, 16, 16, 384, 128, 3),
+    ("d2_conv1_192_64", 1, 32, 32, 192,  64, 3),
+    ("d3_conv1_128_32", 1, 64, 64, 128,  32, 3),
+    ("d3_conv2_32_32",  1, 64, 64,  32,  32, 3),
+    ("d4_conv1_32_16",  1, 64, 128, 32,  16, 3),
+    ("d4_conv2_16_16",  1, 64, 128, 16,  16, 3),
+    ("r50_1x1_256_64",  1, 32, 32, 256,  64, 1),
+    ("r50_1x1_64_256",  1, 32, 32,  64, 256, 1),
+    ("ragged_24_96_48", 3, 24, 40,  96,  48, 3),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=[c[0] for c in DGRAD_CASES])
+def test_native_dgrad_matches_fp32_conv_backward(case, cuda_device):
+    """_ConvFn.backward's data gradient (forward kernel on gy with ``dgrad_weights``) against fp32 autograd of the same
+    conv on the same bf16-rounded operands; tolerance of the per-operator tests (one bf16 rounding of the fp32 result)."""
+    from unet_watermark_b200.training import _ConvFn, native_dgrad_applies
+    name, n, h, w, cin, cout, k = case
+    g = torch.Generator().manual_seed(len(name) * 131 + cin)
+    x = torch.randn(n, cin, h, w, generator=g).to(cuda_device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cout * k * k) ** 0.5).to(cuda_device).to(torch.bfloat16).float()
+    gy = torch.randn(n, cout, h, w, generator=g).to(cuda_device).to(torch.bfloat16)
+    assert native_dgrad_applies(wt.shape, 1, k // 2)
+    x.requires_grad_(True)
+    wp = wt.clone().requires_grad_(True)
+    before = _lib.load().uwm_kernel_launch_count()
+    y = _ConvFn.apply(x, wp, 1, k // 2)
+    y.backward(gy)
+    assert _lib.load().uwm_kernel_launch_count() - before == 2           # forward conv + data-gradient conv
+    x32 = x.detach().float().requires_grad_(True)
+    w32 = wt.clone().requires_grad_(True)
+    torch.nn.functional.conv2d(x32, w32, padding=k // 2).backward(gy.float())
+    err = (x.grad.float() - x32.grad).abs()
+    assert bool((err <= 1e-2 * x32.grad.abs().clamp_min(1.0)).all()), f"dgrad max err {err.max().item()}"
+    werr = (wp.grad - w32.grad).abs()
+    assert bool((werr <= 2e-2 * w32.grad.abs().clamp_min(1.0)).all()), f"wgrad max err {werr.max().item()}"
+
+
+def test_native_dgrad_switch_and_strided_convs_stay_on_cudnn(cuda_device, monkeypatch):
+    from unet_watermark_b200.training import _ConvFn, native_dgrad_applies
+    assert not native_dgrad_applies((128, 64, 3, 3), 2, 1) and not native_dgrad_applies((128, 64, 1, 1), 2, 0)
+    x = torch.randn(2, 64, 16, 16, device=cuda_device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, 64, 3, 3, device=cuda_device) / 24
+    grads = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("UWM_NATIVE_DGRAD", flag)
+        xi = x.clone().requires_grad_(True)
+        before = _lib.load().uwm_kernel_launch_count()
+        _ConvFn.apply(xi, w.clone().requires_grad_(True), 1, 1).sum().backward()
+        assert _lib.load().uwm_kernel_launch_count() - before == (2 if flag == "1" else 1)
+        grads.append(xi.grad.float())
+    assert (grads[0] - grads[1]).abs().max() <= 2e-2 * grads[1].abs().max()

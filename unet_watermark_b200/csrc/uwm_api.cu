@@ -137,6 +137,9 @@ static void launch_pdl_pairs(void (*kernel)(KArgs...), unsigned grid, unsigned b
 
 // per-device caches (a process may drive several GPUs through separate engines)
 constexpr int kMaxDevices = 64;
+// cached CUDA graphs per (model, batch): one per distinct (input, output, threshold) argument set; a caller that rotates
+// 12 input buffers through 8 sub-batches (Engine.forward sub_batch) needs 96
+constexpr size_t kMaxGraphsPerPlan = 512;
 static int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1991,7 +1994,7 @@ extern "C" int uwm_model_forward(uwm_model* m, const void* d_in, int in_fmt, int
   const GraphKey key{d_in, d_logits, d_mask, in_fmt, apply_sigmoid, thr_bits};
   auto git = pl.graphs.find(key);
   if (git == pl.graphs.end()) {
-    if (pl.graphs.size() >= 64) {          // callers that rotate through unbounded pointer sets: start over
+    if (pl.graphs.size() >= kMaxGraphsPerPlan) {          // callers that rotate through unbounded pointer sets: start over
       for (auto& kv : pl.graphs) cudaGraphExecDestroy(kv.second);
       pl.graphs.clear();
     }

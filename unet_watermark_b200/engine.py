@@ -106,10 +106,15 @@ class Engine:
     # -- forward ----------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, want_logits: bool = True, threshold: Optional[float] = None,
                 sigmoid_threshold: bool = True, apply_sigmoid: bool = False, use_graph: bool = True,
-                logits_out: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None
-                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+                logits_out: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None,
+                sub_batch: int = 0) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """x: fp32 [B,3,H,W] (normalised) or uint8 [B,H,W,3] on this engine's device.
-        Returns (fp32 [B,1,H,W] logits or None, uint8 [B,H,W] 0/255 mask or None)."""
+        Returns (fp32 [B,1,H,W] logits or None, uint8 [B,H,W] 0/255 mask or None).
+
+        ``sub_batch`` (0 = off): run the batch as consecutive forwards of at most that many images on slices of the same
+        input / output buffers.  Images are independent in eval mode (SURVEY.md §8e), so the result is bit-identical;
+        what changes is that a layer's hand-over tensor (B x 18.9 MB for resnet50 layer1 at 768x768) fits the 126 MB L2
+        between its producer and its consumer."""
         if not self.weights_loaded:
             raise RuntimeError("Engine.forward before load_weights")
         if not x.is_cuda:
@@ -132,11 +137,15 @@ class Engine:
         if threshold is not None:
             mask = mask_out if mask_out is not None else torch.empty(b, h, w, dtype=torch.uint8, device=x.device)
             thr_logit = logit(threshold) if sigmoid_threshold else float(threshold)
-        rc = self.lib.uwm_model_forward(self.handle, x.data_ptr(), fmt, b,
-                                        logits.data_ptr() if logits is not None else None, int(apply_sigmoid),
-                                        mask.data_ptr() if mask is not None else None, thr_logit, int(use_graph),
-                                        torch.cuda.current_stream(x.device).cuda_stream)
-        _lib.check(rc, "uwm_model_forward")
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        step = b if not sub_batch or sub_batch >= b else int(sub_batch)
+        px, pl, pm = x.data_ptr(), (logits.data_ptr() if logits is not None else 0), (mask.data_ptr() if mask is not None else 0)
+        in_img = h * w * 3 * x.element_size()                       # bytes per image: input / fp32 logits / uint8 mask
+        for i in range(0, b, step):
+            rc = self.lib.uwm_model_forward(self.handle, px + i * in_img, fmt, min(step, b - i),
+                                            pl + i * h * w * 4 if pl else None, int(apply_sigmoid),
+                                            pm + i * h * w if pm else None, thr_logit, int(use_graph), stream)
+            _lib.check(rc, "uwm_model_forward")
         return logits, mask
 
     def read_tensor(self, name: str, batch: int) -> torch.Tensor:

@@ -8,14 +8,18 @@ What runs where
             bf16 NHWC, fp32 accumulation), as a ``torch.autograd.Function``.  BatchNorm runs in TRAIN mode (batch
             statistics, running-stat update) - so it cannot be folded into the conv as the inference plan does - through
             the model's own ``nn.BatchNorm2d`` modules; ReLU / max-pool / nearest-upsample / concat are torch ops.
-  backward  torch autograd: ``aten.convolution_backward`` (cuDNN dgrad / wgrad) on the saved bf16 tensors.  Hand-written
-            dgrad / wgrad kernels are the next step, not part of this round.
+  backward  data gradients of the stride-1 convs (39 of the 45 convs of Unet-resnet34 that run on the C ABI) run on the same tcgen05
+            kernel: dgrad of a 'same' conv is the conv of gy with the flipped, in/out-transposed filter (``dgrad_weights``;
+            ``UWM_NATIVE_DGRAD=0`` turns it off).  Weight gradients, and the data gradients of the stride-2 convs, are
+            ``aten.convolution_backward`` (cuDNN) on the saved bf16 tensors; a hand-written wgrad (K = pixels, both
+            operands MN-major) is the remaining part of SURVEY.md §8 N4.
   exchange  :class:`GradBuckets` - flat fp32 gradient buckets (parameters own views into them) all-reduced over NCCL
             as soon as the backward pass has produced every gradient of a bucket, overlapping the rest of the backward;
             the exposed part (the wait after the backward) is measured with CUDA events.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -48,10 +52,39 @@ class _ConvFn(torch.autograd.Function):
         x, w16 = ctx.saved_tensors
         stride, padding = ctx.conf
         gy = gy.contiguous(memory_format=torch.channels_last)
-        gx, gw, _ = torch.ops.aten.convolution_backward(
+        need_gx = ctx.needs_input_grad[0]
+        gx = None
+        if need_gx and native_dgrad_applies(w16.shape, stride, padding):
+            # data gradient of a stride-1 'same' conv = the conv of gy with the spatially flipped, in/out-transposed
+            # filter: the forward's own tcgen05 kernel, K = taps x Cout, N = Cin
+            cin = w16.shape[1]
+            gx = ops.conv2d(gy.permute(0, 2, 3, 1), dgrad_weights(w16), torch.zeros(cin, dtype=torch.float32, device=gy.device),
+                            w16.shape[2], w16.shape[3], 1, padding, relu=False).permute(0, 3, 1, 2)
+            need_gx = False
+        g2, gw, _ = torch.ops.aten.convolution_backward(
             gy, x, w16.contiguous(memory_format=torch.channels_last), None, [stride, stride], [padding, padding], [1, 1],
-            False, [0, 0], 1, [ctx.needs_input_grad[0], True, False])
-        return gx, gw.float() if gw is not None else None, None, None
+            False, [0, 0], 1, [need_gx, True, False])
+        return (gx if gx is not None else g2), gw.float() if gw is not None else None, None, None
+
+
+def native_dgrad_enabled() -> bool:
+    return os.environ.get("UWM_NATIVE_DGRAD", "1") != "0"
+
+
+def native_dgrad_applies(wshape, stride: int, padding: int) -> bool:
+    """Data gradients that run on ``uwm_conv2d_nhwc_bf16``: stride-1 'same' convs (every 3x3 / 1x1 conv of the network
+    but the three stride-2 stage entries and their 1x1 downsamples, whose transposed conv stays on cuDNN)."""
+    cout, cin, kh, kw = wshape
+    return (native_dgrad_enabled() and stride == 1 and kh == kw and kh % 2 == 1 and padding == kh // 2
+            and cin % 16 == 0 and cout % 16 == 0)
+
+
+def dgrad_weights(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] -> UWM_PACK_TAPS weights [Cin][kh*kw][Cout] of the conv that maps gy to gx:
+    ``gx[n,ci,h,w] = sum_{co,r,s} gy[n,co,h+pad-r,w+pad-s] * w[co,ci,r,s]``, i.e. tap (r',s') = (kh-1-r, kw-1-s) of a
+    'same' conv over gy with the roles of Cin and Cout swapped."""
+    cin = w.shape[1]
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, -1).contiguous()
 
 
 def _conv(x: torch.Tensor, m: nn.Conv2d) -> torch.Tensor:

@@ -12,6 +12,7 @@ containers only: their ``forward`` is never called on the inference path.
 from __future__ import annotations
 
 import logging
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import torch
@@ -190,6 +191,7 @@ class Unet(nn.Module):
         self._tensors_gen = -1
         self._tensors: list = []
         self.use_cuda_graph = True
+        self.sub_batch: Optional[int] = None      # None: UWM_SUBBATCH or the measured rule of _sub_batch_for; 0: never
 
     # smp SegmentationModel.initialize(): decoder kaiming-uniform, head xavier-uniform
     def _initialize(self):
@@ -243,6 +245,23 @@ class Unet(nn.Module):
             eng._token = tok
         return eng
 
+    # hand-over tensors of a whole batch beyond this many input pixels no longer fit the 126 MB L2; (encoder ->
+    # (pixel budget per sub-forward), from the sub-batch sweep of tools/gpu_subbatch_sweep.py (profiles/)
+    _SUB_BATCH_PIXELS: Dict[str, int] = {}
+
+    def _sub_batch_for(self, b: int, h: int, w: int) -> int:
+        """Images per forward launch sequence (see Engine.forward): explicit attribute, else ``UWM_SUBBATCH``, else
+        the measured per-encoder pixel budget.  0 / >= b: the whole batch in one plan."""
+        sb = self.sub_batch
+        if sb is None:
+            env = os.environ.get("UWM_SUBBATCH", "")
+            if env:
+                sb = int(env)
+            else:
+                budget = self._SUB_BATCH_PIXELS.get(self.encoder_name, 0)
+                sb = max(1, budget // (h * w)) if budget else 0
+        return 0 if not sb or sb >= b else int(sb)
+
     def _apply(self, fn, *a, **k):
         self._weights_gen += 1
         return super()._apply(fn, *a, **k)
@@ -284,7 +303,8 @@ class Unet(nn.Module):
             return eng.forward(x, want_logits=want_logits, threshold=threshold,
                                sigmoid_threshold=sigmoid_threshold,
                                apply_sigmoid=(self.activation_name == "sigmoid" or force_sigmoid),
-                               use_graph=self.use_cuda_graph, mask_out=mask_out)
+                               use_graph=self.use_cuda_graph, mask_out=mask_out,
+                               sub_batch=self._sub_batch_for(b, h, w))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """eval mode: the fused inference plan (BatchNorm folded, no autograd), as the reference runs it under
