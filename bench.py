@@ -211,6 +211,35 @@ def cpu_train_reference_run(steps: int, warmup: int, images_per_step: int):
     return images_per_step * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def roofline_by_bound(launch_rows, peaks, step_ms):
+    """Which roofline binds each launch of the step, layer by layer: a launch is HBM-bound when its algorithmic bytes
+    (input + output + residual + weights, each once) / measured copy bandwidth exceed its algorithmic FLOPs / measured
+    bf16 peak.  Per-launch times come from the eager CUDA-event pass and are scaled to the timed (graph-replayed) step.
+    ``floor_ms`` = sum of the per-launch roofline floors = what an unfused layer-by-layer execution could reach."""
+    pt, pb = peaks["bf16_tflops"] * 1e12, peaks["hbm_gbs"] * 1e9
+    eager = sum(r[0] for r in launch_rows)
+    scale = step_ms / eager if eager > 0 else 0.0
+    out = {"hbm": [0.0, 0.0, 0], "tensor": [0.0, 0.0, 0]}          # [ms in the timed step, work, launches]
+    floor = 0.0
+    for ms, fl, by in launch_rows:
+        t_t, t_b = fl / pt * 1e3, by / pb * 1e3
+        floor += max(t_t, t_b)
+        k = "hbm" if t_b > t_t else "tensor"
+        out[k][0] += ms * scale
+        out[k][1] += by if k == "hbm" else fl
+        out[k][2] += 1
+    h, t = out["hbm"], out["tensor"]
+    gbs = h[1] / (h[0] * 1e-3) / 1e9 if h[0] > 0 else 0.0
+    tfs = t[1] / (t[0] * 1e-3) / 1e12 if t[0] > 0 else 0.0
+    return {"hbm_bound": {"launches": h[2], "time_share": h[0] / step_ms if step_ms > 0 else 0.0, "achieved_gbs": gbs,
+                          "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]},
+            "tensor_bound": {"launches": t[2], "time_share": t[0] / step_ms if step_ms > 0 else 0.0,
+                             "achieved_tflops": tfs, "frac_of_bf16_peak": tfs / peaks["bf16_tflops"]},
+            "floor_ms": floor, "step_over_floor": step_ms / floor if floor > 0 else None,
+            "how": "per launch: max(algorithmic FLOPs / bf16 peak, algorithmic bytes / HBM copy peak); eager CUDA-event "
+                   "times scaled by (timed step / eager sum); floor_ms = sum of the per-launch floors (no cross-layer fusion)"}
+
+
 def run_train(args):
     """BASELINE configs[4]: one optimisation step per 'step' (forward in train mode on the tcgen05 conv kernels,
     Dice+BCE, torch-autograd backward, bucketed NCCL gradient all-reduce overlapped with the backward, Adam)."""
@@ -532,10 +561,15 @@ def run_ours(args):
     conv_ms = conv_flops = other_ms = 0.0
     reps = 5
     per_kernel = {}
+    launch_rows = []                                   # per launch of the plan: [mean ms, algorithmic FLOPs, algorithmic bytes]
     for r in range(reps + 1):
         prof = eng.profile(dev_pool[r % n_pool], 0.5)
         if r == 0:
+            launch_rows = [[0.0, fl, by] for _, _, fl, by in prof]
             continue                                   # warm-up pass
+        for i, (_, ms, _, _) in enumerate(prof):
+            if i < len(launch_rows):
+                launch_rows[i][0] += ms / reps
         for name, ms, fl, by in prof:
             if fl > 0:
                 conv_ms += ms
@@ -576,6 +610,10 @@ def run_ours(args):
                 "eager_events": {"conv_ms_per_step": conv_ms / reps, "glue_ms_per_step": other_ms / reps,
                                  "achieved": achieved_eager},
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
+    try:
+        roofline["by_bound"] = roofline_by_bound(launch_rows, peaks, step_ms)
+    except Exception as exc:  # noqa: BLE001 - an explanatory extra must never cost the bench line
+        roofline["by_bound"] = {"error": str(exc)}
 
     if rank == 0:
         value = world * BATCH * args.steps / (ms_total * 1e-3)

@@ -305,6 +305,31 @@ int uwm_mask_components(const uint8_t* d_masks, const uwm_image_desc* h_desc, co
 int uwm_mask_component_summary(const uint8_t* d_masks, const uwm_image_desc* h_desc, const uwm_image_desc* d_desc, int n,
                                int32_t* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training-step glue (BASELINE.json configs[4]; reference src/train.py:68-127 runs the smp Unet under
+ * model.train(): every Conv2dReLU is conv -> BatchNorm2d with BATCH statistics -> ReLU, every residual block ends in
+ * BatchNorm -> add -> ReLU).  NHWC bf16 rows of c channels (c a multiple of 8, <= 2048), dense (pixel pitch c). ---- */
+
+/* y = [relu](BatchNorm2d_train(x) [+ residual]).  d_save[4][c] receives {batch mean, 1/sqrt(biased var + eps),
+ * scale = gamma * rstd, shift = beta - mean * scale} for the backward; running_mean / running_var (both or neither)
+ * are updated in place like torch.nn.BatchNorm2d (momentum, unbiased variance).  d_ws: 2*c doubles that must be ZERO
+ * on entry and are left zero on exit (cross-block fp64 sums). */
+int uwm_bn_train_forward_nhwc_bf16(const void* d_x, long long pixels, int c, const float* d_gamma, const float* d_beta,
+                                   float* d_running_mean, float* d_running_var, float momentum, float eps,
+                                   const void* d_residual, int relu, void* d_y, float* d_save, double* d_ws, void* stream);
+
+/* Backward of the above: g = dy * [y > 0] (when relu), dbeta = sum g, dgamma = sum g * xhat,
+ * dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)), d_residual = g (when has_residual; d_y is then the
+ * forward's output, otherwise the ReLU mask is recomputed from x and d_y may be NULL).  d_coef: 2*c floats scratch;
+ * d_ws as above. */
+int uwm_bn_train_backward_nhwc_bf16(const void* d_dy, const void* d_x, const void* d_y, long long pixels, int c,
+                                    const float* d_save, int relu, int has_residual, void* d_dx, void* d_dres,
+                                    float* d_dgamma, float* d_dbeta, float* d_coef, double* d_ws, void* stream);
+
+/* Backward of uwm_upsample2x_nhwc_bf16: dx[n,h,w,0:c) = sum of the 2x2 block of dy[n,2h,2w,0:c) (dy may be the leading
+ * channel slice of the concat's gradient: pixel pitch dy_pitch). */
+int uwm_upsample2x_backward_nhwc_bf16(const void* d_dy, int n, int h, int w, int c, int dy_pitch, void* d_dx, int dx_pitch,
+                                      void* stream);
+
 /* ---- bench tools: exported only by the tools build of the library (-DUWM_BENCH_TOOLS; python -m
  * unet_watermark_b200.build --tools -> lib/libuwm_b200_tools.so).  The product library has none of these, nor the
  * UWM_DBG pipeline-isolation switches. ---- */

@@ -170,3 +170,92 @@ def test_native_dgrad_switch_and_strided_convs_stay_on_cudnn(cuda_device, monkey
         assert _lib.load().uwm_kernel_launch_count() - before == (2 if flag == "1" else 1)
         grads.append(xi.grad.float())
     assert (grads[0] - grads[1]).abs().max() <= 2e-2 * grads[1].abs().max()
+
+
+# train-mode BatchNorm (+ residual)(+ ReLU) on csrc/uwm_train.cu: (name, n, h, w, c, relu, residual)
+BN_CASES = [
+    ("c16_fullres",   2, 64, 128,  16, True,  False),
+    ("c32",           2, 64,  64,  32, True,  False),
+    ("c64_res",       2, 32,  32,  64, True,  True),
+    ("c128_res",      2, 16,  16, 128, True,  True),
+    ("c256_norelu",   2,  8,   8, 256, False, False),     # downsample branch: BatchNorm only
+    ("c512_res",      4,  4,   4, 512, True,  True),
+    ("c48_ragged",    3, 24,  40,  48, True,  False),     # 6 channel groups: 252-thread blocks
+    ("c2048_res",     1,  4,   4, 2048, True, True),      # resnet50 layer4 expansion
+    ("one_row_each",  1,  1,   3,  64, True,  True),      # fewer pixels than rows per block
+    ("many_rows",     4, 128, 128, 64, True,  True),      # several grid-stride iterations per thread
+]
+
+
+@pytest.mark.parametrize("case", BN_CASES, ids=[c[0] for c in BN_CASES])
+def test_native_batchnorm_matches_torch(case, cuda_device):
+    """_BNFn (forward, running statistics, every gradient) against torch.nn.BatchNorm2d in fp32 on the same bf16-rounded
+    operands.  Outputs are bf16: |err| <= 1e-2 * max(1, |ref|); per-channel sums are fp32-exact to ~1e-5 relative."""
+    from unet_watermark_b200.training import _BNFn
+    name, n, h, w, c, relu, with_res = case
+    g = torch.Generator().manual_seed(c * 7 + h)
+    dev = cuda_device
+    x = (torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(n, c, h, w, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if with_res else None
+    gy = torch.randn(n, c, h, w, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(c).to(dev).train()
+    ref = torch.nn.BatchNorm2d(c).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5); bn.bias.copy_(torch.randn(c, generator=g) * 0.3)
+        bn.running_mean.copy_(torch.randn(c, generator=g)); bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    ref.load_state_dict(bn.state_dict())
+    xi = x.clone().requires_grad_(True)
+    ri = res.clone().requires_grad_(True) if with_res else None
+    v0 = bn.running_mean._version
+    before = _lib.load().uwm_kernel_launch_count()
+    y = _BNFn.apply(xi, bn.weight, bn.bias, ri, bn, relu)
+    y.backward(gy)
+    assert _lib.load().uwm_kernel_launch_count() - before == 6
+    assert bn.running_mean._version > v0 and int(bn.num_batches_tracked) == 1
+    x32 = x.float().requires_grad_(True)
+    r32 = res.float().requires_grad_(True) if with_res else None
+    y32 = ref(x32)
+    if with_res:
+        y32 = y32 + r32
+    if relu:
+        y32 = y32.relu()
+    # the reference masks the gradient where ITS output is positive; compare away from the bf16-rounding boundary
+    y32.backward(gy.float())
+    tol = lambda r: 1e-2 * r.abs().clamp_min(1.0)      # noqa: E731
+    assert y.dtype == torch.bfloat16 and y.shape == x.shape
+    assert bool(((y.float() - y32).abs() <= tol(y32)).all()), (y.float() - y32).abs().max().item()
+    assert torch.allclose(bn.running_mean, ref.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bn.running_var, ref.running_var, rtol=1e-4, atol=1e-5)
+    same_mask = (y.float() > 0) == (y32 > 0) if relu else torch.ones_like(y32, dtype=torch.bool)
+    assert same_mask.float().mean() > 0.999
+    sums_tol = 2e-2 * (n * h * w) ** 0.5 + 1e-3                                 # bf16 masks differ on a few boundary pixels
+    assert bool(((bn.bias.grad - ref.bias.grad).abs() <= 1e-3 * ref.bias.grad.abs() + sums_tol).all())
+    assert bool(((bn.weight.grad - ref.weight.grad).abs() <= 1e-3 * ref.weight.grad.abs() + 3 * sums_tol).all())
+    dxe = (xi.grad.float() - x32.grad).abs()
+    assert bool((dxe[same_mask] <= 2e-2 * x32.grad.abs().clamp_min(1.0)[same_mask]).all()), dxe[same_mask].max().item()
+    if with_res:
+        dre = (ri.grad.float() - r32.grad).abs()
+        assert bool((dre[same_mask] <= tol(r32.grad)[same_mask]).all())
+
+
+def test_native_upcat_matches_torch(cuda_device):
+    from unet_watermark_b200.training import _UpCatFn
+    g = torch.Generator().manual_seed(5)
+    for n, h, w, cx, cs in ((2, 8, 12, 64, 32), (1, 16, 16, 32, 0), (3, 5, 7, 16, 48)):
+        x = torch.randn(n, cx, h, w, generator=g).to(cuda_device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        s = torch.randn(n, cs, 2 * h, 2 * w, generator=g).to(cuda_device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if cs else None
+        gy = torch.randn(n, cx + cs, 2 * h, 2 * w, generator=g).to(cuda_device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        xi = x.clone().requires_grad_(True)
+        si = s.clone().requires_grad_(True) if cs else None
+        y = _UpCatFn.apply(xi, si)
+        y.backward(gy)
+        x32 = x.float().requires_grad_(True)
+        s32 = s.float().requires_grad_(True) if cs else None
+        r = torch.nn.functional.interpolate(x32, scale_factor=2, mode="nearest")
+        if cs:
+            r = torch.cat([r, s32], 1)
+        r.backward(gy.float())
+        assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y.float(), r)
+        assert bool(((xi.grad.float() - x32.grad).abs() <= 1e-2 * x32.grad.abs().clamp_min(1.0)).all())
+        if cs:
+            assert torch.equal(si.grad.float(), s32.grad)

@@ -97,6 +97,11 @@ SIGNATURES = {
     "uwm_mask_morphology": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "uwm_mask_components": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "uwm_mask_component_summary": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    "uwm_bn_train_forward_nhwc_bf16": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, _P,
+                                                 C.c_int, _P, _P, _P, _P]),
+    "uwm_bn_train_backward_nhwc_bf16": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P,
+                                                  _P, _P, _P, _P]),
+    "uwm_upsample2x_backward_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
 }
 
 # exported only by the tools build (-DUWM_BENCH_TOOLS); bound when present

@@ -20,6 +20,7 @@ HEADER = os.path.join("..", "..", "include", "uwm.h")
 UNITS = {
     "uwm_api.cu": ["uwm_api.cu", "conv_tc.cuh", "conv_halo.cuh", "glue.cuh", "ptx_sm100.cuh", "microbench.cuh", HEADER],
     "uwm_imgproc.cu": ["uwm_imgproc.cu", HEADER],
+    "uwm_train.cu": ["uwm_train.cu", HEADER],
 }
 SOURCES = list(UNITS)
 

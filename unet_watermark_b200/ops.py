@@ -252,3 +252,69 @@ def prep_input(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(n, h // 2, w // 2, 16, dtype=torch.bfloat16, device=x.device)
     _lib.check(lib.uwm_prep_input(x.data_ptr(), fmt, n, h, w, out.data_ptr(), _stream()), "uwm_prep_input")
     return out
+
+
+# ---- training-step glue (csrc/uwm_train.cu) ------------------------------------------------------------------------
+_BN_WS: dict = {}
+
+
+def _bn_workspace(device: torch.device) -> torch.Tensor:
+    """2 x 2048 fp64 cross-block sums per (device, stream); the kernels leave them zeroed."""
+    key = (device.index, _stream())
+    ws = _BN_WS.get(key)
+    if ws is None:
+        ws = _BN_WS[key] = torch.zeros(2 * 2048, dtype=torch.float64, device=device)
+    return ws
+
+
+def bn_train_forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
+                     running_var: Optional[torch.Tensor], momentum: float, eps: float, relu: bool,
+                     residual: Optional[torch.Tensor] = None):
+    """[relu](BatchNorm2d with batch statistics (x) [+ residual]) on dense NHWC bf16; updates the running statistics in
+    place.  Returns (y, save) with save = fp32 [4, C]: batch mean, rstd, scale, shift (for bn_train_backward)."""
+    _require_cuda(x, gamma, beta, running_mean, running_var, residual)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    assert residual is None or (residual.is_contiguous() and residual.shape == x.shape and residual.dtype == x.dtype)
+    lib = _lib.load()
+    c = x.shape[3]
+    y = torch.empty_like(x)
+    save = torch.empty(4, c, dtype=torch.float32, device=x.device)
+    rc = lib.uwm_bn_train_forward_nhwc_bf16(
+        x.data_ptr(), x.numel() // c, c, gamma.data_ptr(), beta.data_ptr(),
+        running_mean.data_ptr() if running_mean is not None else None,
+        running_var.data_ptr() if running_var is not None else None, float(momentum), float(eps),
+        residual.data_ptr() if residual is not None else None, int(relu), y.data_ptr(), save.data_ptr(),
+        _bn_workspace(x.device).data_ptr(), _stream())
+    _lib.check(rc, "uwm_bn_train_forward_nhwc_bf16")
+    return y, save
+
+
+def bn_train_backward(dy: torch.Tensor, x: torch.Tensor, y: Optional[torch.Tensor], save: torch.Tensor, relu: bool,
+                      has_residual: bool):
+    """Backward of bn_train_forward: (dx, d_residual or None, dgamma, dbeta)."""
+    _require_cuda(dy, x, y, save)
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype == torch.bfloat16
+    assert not has_residual or (y is not None and y.is_contiguous())
+    lib = _lib.load()
+    c = x.shape[3]
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if has_residual else None
+    grads = torch.empty(4, c, dtype=torch.float32, device=x.device)        # dgamma, dbeta, 2 x coefficient scratch
+    rc = lib.uwm_bn_train_backward_nhwc_bf16(
+        dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None, x.numel() // c, c, save.data_ptr(),
+        int(relu), int(has_residual), dx.data_ptr(), dres.data_ptr() if dres is not None else None,
+        grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), _bn_workspace(x.device).data_ptr(), _stream())
+    _lib.check(rc, "uwm_bn_train_backward_nhwc_bf16")
+    return dx, dres, grads[0], grads[1]
+
+
+def upsample2x_backward(dy: torch.Tensor) -> torch.Tensor:
+    """Backward of nearest 2x: dy [N,2h,2w,C] (may be the leading channel slice of a wider buffer) -> [N,h,w,C]."""
+    _require_cuda(dy)
+    lib = _lib.load()
+    n, h2, w2, c = dy.shape
+    dx = torch.empty(n, h2 // 2, w2 // 2, c, dtype=torch.bfloat16, device=dy.device)
+    rc = lib.uwm_upsample2x_backward_nhwc_bf16(dy.data_ptr(), n, h2 // 2, w2 // 2, c, _pitch(dy), dx.data_ptr(), c, _stream())
+    _lib.check(rc, "uwm_upsample2x_backward_nhwc_bf16")
+    return dx

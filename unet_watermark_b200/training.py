@@ -6,8 +6,10 @@ What runs where
   forward   every convolution whose channel counts are multiples of 16 (all but the 3-channel stem and the 1-channel
             head) runs on the hand-written tcgen05 implicit-GEMM kernel through the C ABI (``uwm_conv2d_nhwc_bf16``:
             bf16 NHWC, fp32 accumulation), as a ``torch.autograd.Function``.  BatchNorm runs in TRAIN mode (batch
-            statistics, running-stat update) - so it cannot be folded into the conv as the inference plan does - through
-            the model's own ``nn.BatchNorm2d`` modules; ReLU / max-pool / nearest-upsample / concat are torch ops.
+            statistics, running-stat update) - so it cannot be folded into the conv as the inference plan does - on the
+            hand-written HBM-bound kernels of csrc/uwm_train.cu, fused with the ReLU and the residual add (``_BNFn``;
+            parameters and running statistics are the model's own ``nn.BatchNorm2d`` modules'); the decoder's nearest
+            upsample is written straight into the concat buffer (``_UpCatFn``); max-pool is a torch op.
   backward  data gradients of the stride-1 convs (39 of the 45 convs of Unet-resnet34 that run on the C ABI) run on the same tcgen05
             kernel: dgrad of a 'same' conv is the conv of gy with the flipped, in/out-transposed filter (``dgrad_weights``;
             ``UWM_NATIVE_DGRAD=0`` turns it off).  Weight gradients, and the data gradients of the stride-2 convs, are
@@ -30,6 +32,18 @@ import torch.nn.functional as F
 from . import ops
 
 
+_ZERO_BIAS: dict = {}
+
+
+def _zero_bias(c: int, device: torch.device) -> torch.Tensor:
+    """fp32 zeros [c] for the bias-free convs (one tensor per (c, device) instead of a fill launch per conv call)."""
+    key = (c, device.index)
+    z = _ZERO_BIAS.get(key)
+    if z is None:
+        z = _ZERO_BIAS[key] = torch.zeros(c, dtype=torch.float32, device=device)
+    return z
+
+
 class _ConvFn(torch.autograd.Function):
     """y = conv2d(x, w) (no bias) on the tcgen05 kernel; x, y: NCHW-shaped channels_last bf16 tensors."""
 
@@ -41,8 +55,7 @@ class _ConvFn(torch.autograd.Function):
             xn = xn.contiguous()
         cout, _, kh, kw = weight.shape
         wp = w16.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()   # UWM_PACK_TAPS ([cout][kh*kw][cin]), packed on the device
-        zero = torch.zeros(cout, dtype=torch.float32, device=x.device)
-        y = ops.conv2d(xn, wp, zero, kh, kw, stride, padding, relu=False)
+        y = ops.conv2d(xn, wp, _zero_bias(cout, x.device), kh, kw, stride, padding, relu=False)
         ctx.save_for_backward(x, w16)
         ctx.conf = (stride, padding)
         return y.permute(0, 3, 1, 2)
@@ -58,7 +71,7 @@ class _ConvFn(torch.autograd.Function):
             # data gradient of a stride-1 'same' conv = the conv of gy with the spatially flipped, in/out-transposed
             # filter: the forward's own tcgen05 kernel, K = taps x Cout, N = Cin
             cin = w16.shape[1]
-            gx = ops.conv2d(gy.permute(0, 2, 3, 1), dgrad_weights(w16), torch.zeros(cin, dtype=torch.float32, device=gy.device),
+            gx = ops.conv2d(gy.permute(0, 2, 3, 1), dgrad_weights(w16), _zero_bias(cin, gy.device),
                             w16.shape[2], w16.shape[3], 1, padding, relu=False).permute(0, 3, 1, 2)
             need_gx = False
         g2, gw, _ = torch.ops.aten.convolution_backward(
@@ -95,9 +108,94 @@ def _conv(x: torch.Tensor, m: nn.Conv2d) -> torch.Tensor:
     return F.conv2d(x, m.weight.to(x.dtype), None if m.bias is None else m.bias.to(x.dtype), m.stride, m.padding)
 
 
-def _bn_relu(x, bn: nn.BatchNorm2d, relu: bool = True):
-    y = bn(x)                                                       # train mode: batch statistics + running-stat update
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Dense NHWC view of an NCHW-shaped tensor (a copy only when it is not channels_last already)."""
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+class _BNFn(torch.autograd.Function):
+    """[relu](BatchNorm2d with batch statistics (x) [+ residual]) on csrc/uwm_train.cu: three HBM-bound launches forward
+    (per-channel sums, finalise + running statistics, normalise + add + ReLU), three backward (ReLU mask + sums, finalise,
+    dx / d residual).  torch's channels_last batch-norm kernels took 9.3 ms of a 26.8 ms step at 512x512 x 16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, bn, relu):
+        xn = _nhwc(x.detach())
+        rn = _nhwc(residual.detach()) if residual is not None else None
+        momentum = bn.momentum
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:                                   # cumulative moving average (torch semantics)
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        y, save = ops.bn_train_forward(xn, weight.detach(), bias.detach(),
+                                       bn.running_mean if bn.track_running_stats else None,
+                                       bn.running_var if bn.track_running_stats else None,
+                                       momentum if momentum is not None else 0.0, bn.eps, relu, rn)
+        if bn.track_running_stats:                                  # written through raw pointers: tell autograd's version
+            for t in (bn.running_mean, bn.running_var):              # counters (Unet._token() watches them)
+                torch.autograd.graph.increment_version(t)
+        ctx.save_for_backward(xn, y if rn is not None else None, save)
+        ctx.relu, ctx.has_res = bool(relu), rn is not None
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, y, save = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = ops.bn_train_backward(_nhwc(gy), xn, y, save, ctx.relu, ctx.has_res)
+        return (dx.permute(0, 3, 1, 2), dgamma, dbeta, dres.permute(0, 3, 1, 2) if dres is not None else None, None, None)
+
+
+def native_bn_applies(x: torch.Tensor, bn: nn.BatchNorm2d) -> bool:
+    c = x.shape[1]
+    return (os.environ.get("UWM_NATIVE_BN", "1") != "0" and bn.training and bn.affine and x.is_cuda
+            and x.dtype == torch.bfloat16 and c % 8 == 0 and c <= 2048 and bn.weight.dtype == torch.float32)
+
+
+def _bn_relu(x, bn: nn.BatchNorm2d, relu: bool = True, residual: Optional[torch.Tensor] = None):
+    """relu(bn(x) [+ residual]) with the module's parameters and running statistics (train mode: batch statistics)."""
+    if native_bn_applies(x, bn):
+        return _BNFn.apply(x, bn.weight, bn.bias, residual, bn, relu)
+    y = bn(x)
+    if residual is not None:
+        y = y + residual
     return F.relu(y) if relu else y
+
+
+class _UpCatFn(torch.autograd.Function):
+    """cat([interpolate(x, 2, 'nearest'), skip], 1) (smp DecoderBlock.forward) written once: the upsample kernel stores
+    into the leading channels of the concat buffer, the skip is copied behind it; backward = 2x2 sums of the leading
+    channels of the gradient + a view of the rest."""
+
+    @staticmethod
+    def forward(ctx, x, skip):
+        xn = _nhwc(x.detach())
+        n, h, w, cx = xn.shape
+        cs = skip.shape[1] if skip is not None else 0
+        out = torch.empty(n, 2 * h, 2 * w, cx + cs, dtype=xn.dtype, device=xn.device)
+        ops.upsample2x(xn, out=out[..., :cx] if cs else out)
+        if cs:
+            out[..., cx:].copy_(skip.detach().permute(0, 2, 3, 1))
+        ctx.cx, ctx.cs = cx, cs
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        gn = _nhwc(g)
+        dx = ops.upsample2x_backward(gn[..., :ctx.cx] if ctx.cs else gn).permute(0, 3, 1, 2)
+        dskip = gn[..., ctx.cx:].permute(0, 3, 1, 2) if ctx.cs else None
+        return dx, dskip
+
+
+def _upcat(x: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
+    cs = skip.shape[1] if skip is not None else 0
+    if (os.environ.get("UWM_NATIVE_UPCAT", "1") != "0" and x.is_cuda and x.dtype == torch.bfloat16
+            and x.shape[1] % 8 == 0 and cs % 8 == 0):
+        return _UpCatFn.apply(x, skip)
+    y = F.interpolate(x, scale_factor=2, mode="nearest")
+    if skip is not None:
+        y = torch.cat([y, skip], dim=1)                             # upsampled first, skip second
+    return y.contiguous(memory_format=torch.channels_last)
 
 
 def forward_train(model, x: torch.Tensor) -> torch.Tensor:
@@ -119,18 +217,15 @@ def forward_train(model, x: torch.Tensor) -> torch.Tensor:
             if hasattr(blk, "conv3"):                               # Bottleneck
                 t = _bn_relu(_conv(y, blk.conv1), blk.bn1)
                 t = _bn_relu(_conv(t, blk.conv2), blk.bn2)
-                y = F.relu(_bn_relu(_conv(t, blk.conv3), blk.bn3, relu=False) + idt)
+                y = _bn_relu(_conv(t, blk.conv3), blk.bn3, residual=idt)
             else:                                                   # BasicBlock
                 t = _bn_relu(_conv(y, blk.conv1), blk.bn1)
-                y = F.relu(_bn_relu(_conv(t, blk.conv2), blk.bn2, relu=False) + idt)
+                y = _bn_relu(_conv(t, blk.conv2), blk.bn2, residual=idt)
         feats.append(y)
     skips = feats[::-1]                                             # layer4, layer3, layer2, layer1, stem
     y = skips[0]
     for i, blk in enumerate(model.decoder.blocks):
-        y = F.interpolate(y, scale_factor=2, mode="nearest")
-        if i + 1 < len(skips):
-            y = torch.cat([y, skips[i + 1]], dim=1)                 # upsampled first, skip second
-        y = y.contiguous(memory_format=torch.channels_last)
+        y = _upcat(y, skips[i + 1] if i + 1 < len(skips) else None)
         y = _bn_relu(_conv(y, blk.conv1[0]), blk.conv1[1])
         y = _bn_relu(_conv(y, blk.conv2[0]), blk.conv2[1])
     logits = _conv(y, model.segmentation_head[0]).float()
