@@ -284,7 +284,7 @@ def run_train(args):
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = lib.uwm_kernel_launch_count()
+    l0 = lib.uwm_kernel_launch_count() + ts.replayed_native_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     exposed = []
@@ -294,7 +294,7 @@ def run_train(args):
     e1.record()
     sync_all()
     clocks = sampler.stop()
-    launches = int(lib.uwm_kernel_launch_count() - l0)
+    launches = int(lib.uwm_kernel_launch_count() + ts.replayed_native_launches - l0)
     ms_total = e0.elapsed_time(e1)
     exposed_ms = sum(a.elapsed_time(b) for a, b in exposed) / max(len(exposed), 1)
     final_loss = float(loss)
@@ -323,8 +323,10 @@ def run_train(args):
                 "config": {"workload": WORKLOAD, "baseline_config": 5, "encoder": ENCODER, "image": [SIZE, SIZE],
                            "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                            "loss": "0.5 * Dice(smooth 1e-5) + 0.5 * BCEWithLogits", "optimizer": "Adam lr 1e-4 wd 1e-4",
-                           "forward": "tcgen05 conv kernels (all convs but the 3-channel stem and the 1-channel head) + train-mode BatchNorm",
-                           "backward": "torch autograd (aten.convolution_backward)",
+                           "forward": "tcgen05 conv kernels (all convs but the 3-channel stem and the 1-channel head) + train-mode BatchNorm (+ residual, ReLU) kernels",
+                           "backward": "data gradients of the stride-1 convs on the tcgen05 conv kernel, BatchNorm / ReLU / residual / "
+                                       "upsample backward on hand-written HBM-bound kernels, weight gradients cuDNN (aten.convolution_backward)",
+                           "cuda_graph": bool(ts.use_graph),
                            "l2": f"inputs rotate through {n_pool} batches of {BATCH * 3 * SIZE * SIZE * 4 / 1e6:.0f} MB > 126 MB L2"},
                 "tflops_per_gpu_3x_forward": tf, "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
                 "allreduce": {"bytes_per_step": ts.buckets.bytes, "buckets": len(ts.buckets.buckets),

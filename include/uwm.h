@@ -311,8 +311,9 @@ int uwm_mask_component_summary(const uint8_t* d_masks, const uwm_image_desc* h_d
 
 /* y = [relu](BatchNorm2d_train(x) [+ residual]).  d_save[4][c] receives {batch mean, 1/sqrt(biased var + eps),
  * scale = gamma * rstd, shift = beta - mean * scale} for the backward; running_mean / running_var (both or neither)
- * are updated in place like torch.nn.BatchNorm2d (momentum, unbiased variance).  d_ws: 2*c doubles that must be ZERO
- * on entry and are left zero on exit (cross-block fp64 sums). */
+ * are updated in place like torch.nn.BatchNorm2d (momentum, unbiased variance).  d_ws: UWM_BN_WS_SLOTS*2*c doubles that
+ * must be ZERO on entry and are left zero on exit (cross-block fp64 sums, spread over slots to keep atomics apart). */
+#define UWM_BN_WS_SLOTS 32
 int uwm_bn_train_forward_nhwc_bf16(const void* d_x, long long pixels, int c, const float* d_gamma, const float* d_beta,
                                    float* d_running_mean, float* d_running_var, float momentum, float eps,
                                    const void* d_residual, int relu, void* d_y, float* d_save, double* d_ws, void* stream);

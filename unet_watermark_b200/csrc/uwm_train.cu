@@ -93,15 +93,45 @@ int sm_count() {
   return n[dev];
 }
 
-// block-level fold of 2 x 8 per-thread partial sums into ws[0..c) / ws[c..2c) (fp64 atomics across blocks)
-__device__ __forceinline__ void fold_sums(const float* a, const float* q, int g, int c, float* sm, double* ws) {
+// Fold of the 2 x 8 per-thread partial sums.  Threads of a warp that own the same channel group (lanes g, g + groups, ...:
+// groups divides 32) are combined with xor shuffles first, so shared memory sees one add per warp and channel instead of
+// one per thread (fp32 shared atomics are compare-and-swap loops: 128 threads on one address serialise); across blocks
+// the sums go to one of kSlots copies of ws (blockIdx % kSlots) - 1184 blocks adding fp64 atomics into the SAME eight
+// cache lines took longer than reading the tensor.
+constexpr int kSlots = UWM_BN_WS_SLOTS;
+
+__device__ __forceinline__ void fold_sums(float* a, float* q, int g, int c, int groups, float* sm, double* ws) {
+  const bool shuffled = groups <= 32 && (groups & (groups - 1)) == 0;      // then blockDim = 256: whole warps
+  if (shuffled) {
+    for (int off = groups; off < 32; off <<= 1) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sm[g * 8 + k], a[k]);
-    atomicAdd(&sm[c + g * 8 + k], q[k]);
+      for (int k = 0; k < 8; ++k) {
+        a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+        q[k] += __shfl_xor_sync(0xffffffffu, q[k], off);
+      }
+    }
+  }
+  if (!shuffled || (threadIdx.x & 31) < groups) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sm[g * 8 + k], a[k]);
+      atomicAdd(&sm[c + g * 8 + k], q[k]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&ws[i], (double)sm[i]);
+  double* slot = ws + (size_t)(blockIdx.x % kSlots) * 2 * c;
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&slot[i], (double)sm[i]);
+}
+
+// sum of the kSlots copies of entry i, which are left zeroed for the next call
+__device__ __forceinline__ double take_slots(double* ws, int i, int c) {
+  double s = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < kSlots; ++k) {
+    s += ws[(size_t)k * 2 * c + i];
+    ws[(size_t)k * 2 * c + i] = 0.0;
+  }
+  return s;
 }
 
 // ---- forward ---------------------------------------------------------------------------------------------------
@@ -125,7 +155,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
       q[k] = fmaf(f[k], f[k], q[k]);
     }
   }
-  fold_sums(a, q, g, c, sm, ws);
+  fold_sums(a, q, g, c, groups, sm, ws);
 }
 
 // mean / biased variance -> save_mean, save_rstd, scale = gamma * rstd, shift = beta - mean * scale; running statistics
@@ -135,9 +165,7 @@ __global__ void bn_fwd_finalize_kernel(double* __restrict__ ws, long long pixels
                                        float momentum, float eps, float* __restrict__ save_mean,
                                        float* __restrict__ save_rstd, float* __restrict__ scale, float* __restrict__ shift) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) {
-    const double s = ws[i], ss = ws[c + i];
-    ws[i] = 0.0;
-    ws[c + i] = 0.0;
+    const double s = take_slots(ws, i, c), ss = take_slots(ws, c + i, c);
     const double mean = s / (double)pixels;
     double var = ss / (double)pixels - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -216,7 +244,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
       q[k] = fmaf(gk, f[k] - mu[k], q[k]);
     }
   }
-  fold_sums(a, q, g, c, sm, ws);
+  fold_sums(a, q, g, c, groups, sm, ws);
 }
 
 // dbeta = sum g; dgamma = rstd * sum g (x - mean); coefficients of dx = scale * (g - kb - (x - mean) * kc) with
@@ -225,9 +253,7 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ ws, long long pixels
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ kb,
                                        float* __restrict__ kc) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) {
-    const double sg = ws[i], sgx = ws[c + i];
-    ws[i] = 0.0;
-    ws[c + i] = 0.0;
+    const double sg = take_slots(ws, i, c), sgx = take_slots(ws, c + i, c);
     const double rs = (double)rstd[i];
     dbeta[i] = (float)sg;
     dgamma[i] = (float)(rs * sgx);
@@ -311,7 +337,7 @@ int check_bn(const char* who, const void* a, const void* b, long long pixels, in
 extern "C" int uwm_bn_train_forward_nhwc_bf16(const void* d_x, long long pixels, int c, const float* d_gamma,
                                               const float* d_beta, float* d_running_mean, float* d_running_var,
                                               float momentum, float eps, const void* d_residual, int relu, void* d_y,
-                                              float* d_save /*[4][c]: mean, rstd, scale, shift*/, double* d_ws /*[2][c], zero*/,
+                                              float* d_save /*[4][c]: mean, rstd, scale, shift*/, double* d_ws /*[slots][2][c], zero*/,
                                               void* stream) {
   int rc = check_bn("bn_train_forward", d_x, d_y, pixels, c);
   if (rc) return rc;
@@ -341,7 +367,7 @@ extern "C" int uwm_bn_train_forward_nhwc_bf16(const void* d_x, long long pixels,
 extern "C" int uwm_bn_train_backward_nhwc_bf16(const void* d_dy, const void* d_x, const void* d_y, long long pixels, int c,
                                                const float* d_save /*[4][c] of the forward*/, int relu, int has_residual,
                                                void* d_dx, void* d_dres, float* d_dgamma, float* d_dbeta,
-                                               float* d_coef /*[2][c] scratch*/, double* d_ws /*[2][c], zero*/, void* stream) {
+                                               float* d_coef /*[2][c] scratch*/, double* d_ws /*[slots][2][c], zero*/, void* stream) {
   int rc = check_bn("bn_train_backward", d_dy, d_x, pixels, c);
   if (rc) return rc;
   if (!d_save || !d_dx || !d_dgamma || !d_dbeta || !d_coef || !d_ws)

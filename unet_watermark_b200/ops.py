@@ -259,11 +259,11 @@ _BN_WS: dict = {}
 
 
 def _bn_workspace(device: torch.device) -> torch.Tensor:
-    """2 x 2048 fp64 cross-block sums per (device, stream); the kernels leave them zeroed."""
+    """UWM_BN_WS_SLOTS (32) x 2 x 2048 fp64 cross-block sums per (device, stream); the kernels leave them zeroed."""
     key = (device.index, _stream())
     ws = _BN_WS.get(key)
     if ws is None:
-        ws = _BN_WS[key] = torch.zeros(2 * 2048, dtype=torch.float64, device=device)
+        ws = _BN_WS[key] = torch.zeros(32 * 2 * 2048, dtype=torch.float64, device=device)
     return ws
 
 

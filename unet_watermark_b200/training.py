@@ -15,9 +15,12 @@ What runs where
             ``UWM_NATIVE_DGRAD=0`` turns it off).  Weight gradients, and the data gradients of the stride-2 convs, are
             ``aten.convolution_backward`` (cuDNN) on the saved bf16 tensors; a hand-written wgrad (K = pixels, both
             operands MN-major) is the remaining part of SURVEY.md §8 N4.
-  exchange  :class:`GradBuckets` - flat fp32 gradient buckets (parameters own views into them) all-reduced over NCCL
+  launch    zero_grad + forward + loss + backward replay as ONE CUDA graph per input shape (``TrainStep``; ~1000 launches
+            and ~200 Python autograd-function calls per step are host-bound otherwise; ``UWM_TRAIN_GRAPH=0``: eager).
+  exchange  :class:`GradBuckets` - flat fp32 gradient buckets (parameters own views into them) all-reduced over NCCL:
+            after the graph when the step is graph-replayed (98 MB over NVSwitch is well under a millisecond), or, eager,
             as soon as the backward pass has produced every gradient of a bucket, overlapping the rest of the backward;
-            the exposed part (the wait after the backward) is measured with CUDA events.
+            the exposed part (the wait after the backward) is measured with CUDA events.  Adam is torch's fused kernel.
 """
 from __future__ import annotations
 
@@ -271,6 +274,7 @@ class GradBuckets:
         self._sizes = [len(g) for g in groups]
         self._ready = [0] * len(groups)
         self._works = []
+        self.overlap = True              # False: hooks only count (a CUDA-graph-captured backward); finish(all_buckets=True)
         self.bytes = sum(b.numel() * 4 for b in self.buckets)
 
     def zero_grad(self):
@@ -282,14 +286,15 @@ class GradBuckets:
     def _on_grad(self, p):
         bi = self._bucket_of[p]
         self._ready[bi] += 1
-        if self._ready[bi] == self._sizes[bi] and self.world > 1:
+        if self._ready[bi] == self._sizes[bi] and self.world > 1 and self.overlap:
             self._works.append(dist.all_reduce(self.buckets[bi], group=self.group, async_op=True))
 
-    def finish(self):
-        """Wait for every bucket's all-reduce and turn the sums into means."""
+    def finish(self, all_buckets: bool = False):
+        """Wait for every bucket's all-reduce and turn the sums into means.  ``all_buckets``: nothing was launched
+        from the hooks (graph replay) - reduce every bucket now."""
         if self.world > 1:
             for i, n in enumerate(self._ready):                  # parameters that received no gradient this step
-                if n != self._sizes[i]:
+                if all_buckets or n != self._sizes[i]:
                     self._works.append(dist.all_reduce(self.buckets[i], group=self.group, async_op=True))
             for w in self._works:
                 w.wait()
@@ -307,37 +312,99 @@ class TrainStep:
     """One optimisation step as the reference runs it (src/train.py:82-107), data-parallel over the process group."""
 
     def __init__(self, model, cfg=None, lr: Optional[float] = None, weight_decay: Optional[float] = None,
-                 criterion: Optional[nn.Module] = None, bucket_mb: float = 25.0):
+                 criterion: Optional[nn.Module] = None, bucket_mb: float = 25.0, use_graph: Optional[bool] = None):
         from .config import get_cfg_defaults
         from .losses import dice_bce_from_config
         self.cfg = cfg if cfg is not None else get_cfg_defaults()
         self.model = model
         self.criterion = criterion if criterion is not None else dice_bce_from_config(self.cfg)
         # reference src/train.py:265-270: Adam(lr = TRAIN.LR, weight_decay = TRAIN.WEIGHT_DECAY)
+        # (fused = the same update as one multi-tensor launch per step instead of ~20 foreach launches)
+        on_cuda = all(p.is_cuda for p in model.parameters())
         self.optimizer = torch.optim.Adam(model.parameters(), lr=self.cfg.TRAIN.LR if lr is None else lr,
-                                          weight_decay=self.cfg.TRAIN.WEIGHT_DECAY if weight_decay is None else weight_decay)
+                                          weight_decay=self.cfg.TRAIN.WEIGHT_DECAY if weight_decay is None else weight_decay,
+                                          fused=True if on_cuda else None)
         self.buckets = GradBuckets(model.parameters(), bucket_mb=bucket_mb)
         self.exposed_ms: List[float] = []
+        # CUDA graph of zero_grad + forward + loss + backward per (shape, dtype) of the inputs: ~1000 kernel launches and
+        # ~200 Python autograd-function calls per step are host-bound once the kernels are fast (UWM_TRAIN_GRAPH=0: eager)
+        self.use_graph = os.environ.get("UWM_TRAIN_GRAPH", "1") != "0" if use_graph is None else bool(use_graph)
+        if any(isinstance(m, nn.BatchNorm2d) and m.momentum is None for m in model.modules()):
+            self.use_graph = False            # cumulative-average BatchNorm reads num_batches_tracked on the host
+        self.graph_warmup = 2                 # eager steps on the capture stream before capturing
+        self._graphs: dict = {}
+        self.replayed_native_launches = 0     # libuwm_b200.so kernels run by graph replays (the library counts captures only)
+        self._seen: dict = {}
+        self._stream: Optional[torch.cuda.Stream] = None
+
+    def _forward_backward(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        self.buckets.zero_grad()                                   # optimizer.zero_grad(): grads are bucket views
+        out = self.model(images)
+        loss = self.criterion(out, masks)
+        loss.backward()
+        return loss.detach()
+
+    def _exchange_and_update(self, time_exchange: bool, all_buckets: bool):
+        if time_exchange:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.buckets.finish(all_buckets)
+            e1.record()
+            self._pending = (e0, e1)
+        else:
+            self.buckets.finish(all_buckets)
+        self.optimizer.step()
 
     def step(self, images: torch.Tensor, masks: torch.Tensor, time_exchange: bool = False) -> torch.Tensor:
         """images: fp32 [B,3,H,W] normalised; masks: {0,1} [B,H,W] or [B,1,H,W].  Returns the (detached) loss."""
         self.model.train()
-        self.buckets.zero_grad()                                   # optimizer.zero_grad(): grads are bucket views
-        out = self.model(images)
         if masks.dim() == 3:
             masks = masks.unsqueeze(1)
-        loss = self.criterion(out, masks)
-        loss.backward()
-        if time_exchange and images.is_cuda:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            self.buckets.finish()
-            e1.record()
-            self._pending = (e0, e1)
-        else:
-            self.buckets.finish()
-        self.optimizer.step()
-        return loss.detach()
+        if not (self.use_graph and images.is_cuda):
+            self.buckets.overlap = True
+            loss = self._forward_backward(images, masks)
+            self._exchange_and_update(time_exchange and images.is_cuda, False)
+            return loss
+        return self._step_graph(images, masks, time_exchange)
+
+    def _step_graph(self, images: torch.Tensor, masks: torch.Tensor, time_exchange: bool) -> torch.Tensor:
+        """The same step with zero_grad + forward + loss + backward replayed from one CUDA graph; the gradient exchange
+        (NCCL, after the graph instead of from hooks inside the backward: 98 MB over NVSwitch is ~0.5 ms) and Adam follow it."""
+        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype, images.device.index)
+        cur = torch.cuda.current_stream(images.device)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(images.device)
+        entry = self._graphs.get(key)
+        if entry is None:
+            n = self._seen.get(key, 0)
+            self._seen[key] = n + 1
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                self.buckets.overlap = False
+                if n < self.graph_warmup:                            # eager on the capture stream (allocator, cuDNN plans)
+                    loss = self._forward_backward(images, masks)
+                else:
+                    from . import _lib
+                    sx, st = images.clone(), masks.clone()
+                    g = torch.cuda.CUDAGraph()
+                    l0 = _lib.load().uwm_kernel_launch_count()
+                    with torch.cuda.graph(g, stream=self._stream):
+                        sl = self._forward_backward(sx, st)
+                    # launches of libuwm_b200.so inside the graph (the library counted them at capture = this first replay)
+                    entry = self._graphs[key] = (g, sx, st, sl, int(_lib.load().uwm_kernel_launch_count() - l0))
+                    g.replay()
+                    loss = sl.clone()
+            cur.wait_stream(self._stream)
+            self._exchange_and_update(time_exchange, True)
+            return loss
+        g, sx, st, sl, n_native = entry
+        sx.copy_(images, non_blocking=True)
+        st.copy_(masks, non_blocking=True)
+        g.replay()
+        self.replayed_native_launches += n_native
+        loss = sl.clone()
+        self._exchange_and_update(time_exchange, True)
+        return loss
 
     def exposed_exchange_ms(self) -> float:
         """Device time between the end of the backward pass and the last averaged bucket of the latest step timed with
