@@ -298,14 +298,22 @@ def run_train(args):
     ms_total = e0.elapsed_time(e1)
     exposed_ms = sum(a.elapsed_time(b) for a, b in exposed) / max(len(exposed), 1)
     final_loss = float(loss)
-    # end to end: every step uploads its images + masks from pinned host memory and reads the loss back (loss.item(), :107)
+    # end to end: every step uploads its images + masks from pinned host memory and reads the loss back (loss.item(), :107);
+    # the upload of batch i+1 runs on the prefetcher's copy stream under step i (DataLoader(pin_memory) + .to(device))
+    from unet_watermark_b200.training import DevicePrefetcher
+
+    pf = DevicePrefetcher((), dev)
+
+    def e2e_loop(nsteps):
+        pf.batches = ((host_x[i % n_pool], host_t[i % n_pool]) for i in range(nsteps))
+        for x, t in pf:
+            _ = ts.step(x, t).item()
+
+    e2e_loop(3)                                            # untimed: staging buffers, copy stream
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for i in range(args.steps):
-        x = host_x[i % n_pool].to(dev, non_blocking=True)
-        t = host_t[i % n_pool].to(dev, non_blocking=True)
-        _ = ts.step(x, t).item()
+    e2e_loop(args.steps)                                   # the first upload is exposed and inside the timed region
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
@@ -335,7 +343,8 @@ def run_train(args):
                 "e2e": {"value": world * BATCH * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": world * BATCH * SIZE * SIZE * (3 * 4 + 8), "d2h_bytes_per_step": world * 4,
                         "ms_per_step": ms_e2e / args.steps,
-                        "api": "pinned host fp32 images + int64 masks -> H2D -> TrainStep.step -> loss.item()"},
+                        "api": "pinned host fp32 images + int64 masks -> H2D on the prefetcher's copy stream (DevicePrefetcher, batch i+1 under step i) "
+                               "-> TrainStep.step -> loss.item() every step"},
                 "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
                 "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel / conv_tc_kernel (forward convs of the training step)",
                              "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],

@@ -198,3 +198,13 @@ def test_two_rank_gloo_bucketed_gradient_allreduce_averages():
         want = (torch.tensor(gathered[0][i]) + torch.tensor(gathered[1][i])) / 2
         assert torch.allclose(torch.tensor(a), want, atol=1e-6)
     assert any(gathered[0][i] != gathered[1][i] for i in range(len(avg)))      # the ranks really saw different data
+
+
+def test_device_prefetcher_passes_batches_through_on_cpu():
+    from unet_watermark_b200.training import DevicePrefetcher
+    batches = [(torch.full((2, 3, 4, 4), float(i)), torch.full((2, 4, 4), i, dtype=torch.long)) for i in range(5)]
+    got = [(x.clone(), t.clone()) for x, t in DevicePrefetcher(iter(batches), "cpu")]
+    assert len(got) == 5
+    for (x, t), (gx, gt) in zip(batches, got):
+        assert torch.equal(x, gx) and torch.equal(t, gt)
+    assert list(DevicePrefetcher(iter(()), "cpu")) == []

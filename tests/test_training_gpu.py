@@ -259,3 +259,50 @@ def test_native_upcat_matches_torch(cuda_device):
         assert bool(((xi.grad.float() - x32.grad).abs() <= 1e-2 * x32.grad.abs().clamp_min(1.0)).all())
         if cs:
             assert torch.equal(si.grad.float(), s32.grad)
+
+
+def test_device_prefetcher_uploads_in_order_and_reuses_its_staging(cuda_device):
+    """Host batches arrive on the device intact and in order while later uploads are already in flight; the staging
+    slots survive a second iteration, a shape change and a consumer that stops early."""
+    from unet_watermark_b200.training import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(4, 3, 64, 64, generator=g).pin_memory(),
+                (torch.rand(4, 64, 64, generator=g) > 0.5).long().pin_memory()) for _ in range(7)]
+    pf = DevicePrefetcher(iter(batches), cuda_device)
+    burn = torch.randn(2048, 2048, device=cuda_device)
+    n = 0
+    for (hx, ht), (x, t) in zip(batches, pf):
+        for _ in range(4):
+            burn = burn @ burn * 1e-3                              # keeps the step stream busy while the next upload runs
+        assert x.device.type == "cuda" and torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
+        n += 1
+    assert n == 7
+    pf.batches = iter(batches[:3])
+    for i, (x, t) in enumerate(pf):                                # stop early: the slot is released all the same
+        if i == 1:
+            break
+    small = [(torch.randn(2, 3, 32, 32, generator=g).pin_memory(), torch.zeros(2, 32, 32, dtype=torch.long).pin_memory())
+             for _ in range(3)]
+    pf.batches = iter(batches[:2] + small)
+    got = [(x.cpu(), t.cpu()) for x, t in pf]
+    for (hx, ht), (x, t) in zip(batches[:2] + small, got):
+        assert torch.equal(x, hx) and torch.equal(t, ht)
+    assert list(DevicePrefetcher(iter(()), cuda_device)) == []
+
+
+def test_train_step_from_prefetched_batches_equals_device_resident_batches(cuda_device):
+    """lr = 0 keeps the weights fixed, so step i's loss depends on batch i alone: the prefetched batches are the right
+    ones, in order, through the eager warm-up steps, the capture and the graph replays."""
+    from unet_watermark_b200.training import DevicePrefetcher
+    data = [synthetic_watermark_batch(4, 64, seed=700 + i, device="cpu") for i in range(5)]
+    host = [(x.pin_memory(), t[:, 0].long().pin_memory()) for x, _, t in data]
+    losses = []
+    for use_pf in (False, True):
+        torch.manual_seed(0)
+        m = Unet("resnet34", encoder_weights=None).to(cuda_device)
+        ts = TrainStep(m, lr=0.0, weight_decay=0.0)
+        src = DevicePrefetcher(iter(host), cuda_device) if use_pf else ((x.to(cuda_device), t.to(cuda_device)) for x, t in host)
+        losses.append([float(ts.step(x, t)) for x, t in src])
+    # (not bit-equal: cuDNN's weight-gradient kernels and the BatchNorm sums accumulate with atomics)
+    assert torch.allclose(torch.tensor(losses[0]), torch.tensor(losses[1]), rtol=2e-3), losses
+    assert len(set(round(v, 3) for v in losses[0])) >= 4, losses        # the batches really differ

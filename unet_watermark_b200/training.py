@@ -52,12 +52,16 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, stride, padding):
-        w16 = weight.detach().to(torch.bfloat16)
+        # one cast + permute launch: the channels_last bf16 filter IS the UWM_PACK_TAPS layout ([cout][kh*kw][cin]) and
+        # the layout cuDNN's weight-gradient call wants in the backward (three strided copies per conv before)
+        w16 = weight.detach().to(torch.bfloat16, memory_format=torch.channels_last)
         xn = x.detach().permute(0, 2, 3, 1)                       # NHWC view of the channels_last tensor
         if not xn.is_contiguous():
             xn = xn.contiguous()
         cout, _, kh, kw = weight.shape
-        wp = w16.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()   # UWM_PACK_TAPS ([cout][kh*kw][cin]), packed on the device
+        wp = w16.permute(0, 2, 3, 1).reshape(cout, -1)
+        if not wp.is_contiguous():                                # (1x1 filters: strides of size-1 dims are ambiguous)
+            wp = wp.contiguous()
         y = ops.conv2d(xn, wp, _zero_bias(cout, x.device), kh, kw, stride, padding, relu=False)
         ctx.save_for_backward(x, w16)
         ctx.conf = (stride, padding)
@@ -412,3 +416,66 @@ class TrainStep:
         e0, e1 = self._pending
         e1.synchronize()
         return e0.elapsed_time(e1)
+
+
+class DevicePrefetcher:
+    """Host batches -> device batches with the upload of batch i+1 running on its own stream under step i: the reference's
+    ``DataLoader(pin_memory=True)`` + ``images.to(device)`` / ``masks.to(device)`` (src/train.py:84-87) with the copy
+    taken off the step's stream.  ``batches`` yields ``(images, masks)`` host tensors (pinned, or the copy is
+    synchronous); iterating yields device tensors that stay valid until the next ``depth - 1`` items have been taken.
+    On a CPU device it passes the batches through."""
+
+    def __init__(self, batches, device, depth: int = 2):
+        self.batches = batches
+        self.device = torch.device(device)
+        self.depth = max(int(depth), 2)
+        self._copy: Optional[torch.cuda.Stream] = None
+        self._slots: List[Optional[dict]] = [None] * self.depth     # staging tensors, kept across iterations
+
+    def __iter__(self):
+        dev = self.device
+        if dev.type != "cuda":
+            for x, t in self.batches:
+                yield x.to(dev), t.to(dev)
+            return
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(dev)
+        copy = self._copy
+        slots = self._slots
+
+        def issue(k: int, batch):
+            x, t = batch
+            s = slots[k]
+            if s is None or s["x"].shape != x.shape or s["x"].dtype != x.dtype or s["t"].shape != t.shape or s["t"].dtype != t.dtype:
+                s = slots[k] = {"x": torch.empty(x.shape, dtype=x.dtype, device=dev),
+                                "t": torch.empty(t.shape, dtype=t.dtype, device=dev),
+                                "ready": torch.cuda.Event(), "free": None}
+                copy.wait_stream(torch.cuda.current_stream(dev))     # the allocation's stream
+            with torch.cuda.stream(copy):
+                if s["free"] is not None:
+                    copy.wait_event(s["free"])                      # the step that read this slot last has finished
+                s["x"].copy_(x, non_blocking=True)
+                s["t"].copy_(t, non_blocking=True)
+                s["ready"].record(copy)
+
+        it = iter(self.batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        issue(0, nxt)
+        i = 0
+        while True:
+            k = i % self.depth
+            nxt = next(it, None)
+            if nxt is not None:
+                issue((i + 1) % self.depth, nxt)
+            torch.cuda.current_stream(dev).wait_event(slots[k]["ready"])
+            try:
+                yield slots[k]["x"], slots[k]["t"]
+            finally:                                                # also when the consumer stops early
+                free = torch.cuda.Event()
+                free.record(torch.cuda.current_stream(dev))
+                slots[k]["free"] = free
+            if nxt is None:
+                return
+            i += 1
