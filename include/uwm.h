@@ -331,6 +331,22 @@ int uwm_bn_train_backward_nhwc_bf16(const void* d_dy, const void* d_x, const voi
 int uwm_upsample2x_backward_nhwc_bf16(const void* d_dy, int n, int h, int w, int c, int dy_pitch, void* d_dx, int dx_pitch,
                                       void* stream);
 
+/* Backward of uwm_maxpool3x3s2_nhwc_bf16 / torch MaxPool2d(3, 2, 1): d_x is the pool's INPUT [n,h,w,c] (dense), d_dy the
+ * gradient of its output [n,(h-1)/2+1,(w-1)/2+1,c]; every window's gradient goes to its first maximum in row-major scan
+ * order (torch's arg-max rule, recomputed instead of saved); overlapping windows add in fp32. */
+int uwm_maxpool3x3s2_backward_nhwc_bf16(const void* d_dy, const void* d_x, int n, int h, int w, int c, void* d_dx,
+                                        void* stream);
+
+/* Filters of one training-step conv: fp32 [cout][cin][kh][kw] (the nn.Conv2d parameter) -> bf16 UWM_PACK_TAPS operands
+ * d_fwd [cout][kh*kw][cin] (for uwm_conv2d_nhwc_bf16 on x) and, unless NULL, d_dgrad [cin][kh*kw][cout] with the taps
+ * flipped: uwm_conv2d_nhwc_bf16 on dy with d_dgrad is the data gradient of a stride-1 'same' conv. */
+int uwm_pack_train_weights(const float* d_w, int cout, int cin, int kh, int kw, void* d_fwd, void* d_dgrad, void* stream);
+
+/* dst[p, 0:c) = src[p, 0:c) for p < pixels; rows of src / dst are src_pitch / dst_pitch bf16 apart (the skip half of
+ * smp DecoderBlock's torch.cat([x, skip], 1), and the skip's slice of the concat's gradient); 16-byte aligned bases. */
+int uwm_copy_channels_nhwc_bf16(const void* d_src, long long pixels, int c, int src_pitch, void* d_dst, int dst_pitch,
+                                void* stream);
+
 /* ---- bench tools: exported only by the tools build of the library (-DUWM_BENCH_TOOLS; python -m
  * unet_watermark_b200.build --tools -> lib/libuwm_b200_tools.so).  The product library has none of these, nor the
  * UWM_DBG pipeline-isolation switches. ---- */

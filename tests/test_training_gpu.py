@@ -146,7 +146,7 @@ def test_native_dgrad_matches_fp32_conv_backward(case, cuda_device):
     before = _lib.load().uwm_kernel_launch_count()
     y = _ConvFn.apply(x, wp, 1, k // 2)
     y.backward(gy)
-    assert _lib.load().uwm_kernel_launch_count() - before == 2           # forward conv + data-gradient conv
+    assert _lib.load().uwm_kernel_launch_count() - before == 3           # filter pack + forward conv + data-gradient conv
     x32 = x.detach().float().requires_grad_(True)
     w32 = wt.clone().requires_grad_(True)
     torch.nn.functional.conv2d(x32, w32, padding=k // 2).backward(gy.float())
@@ -167,7 +167,7 @@ def test_native_dgrad_switch_and_strided_convs_stay_on_cudnn(cuda_device, monkey
         xi = x.clone().requires_grad_(True)
         before = _lib.load().uwm_kernel_launch_count()
         _ConvFn.apply(xi, w.clone().requires_grad_(True), 1, 1).sum().backward()
-        assert _lib.load().uwm_kernel_launch_count() - before == (2 if flag == "1" else 1)
+        assert _lib.load().uwm_kernel_launch_count() - before == (3 if flag == "1" else 2)   # filter pack, conv(s)
         grads.append(xi.grad.float())
     assert (grads[0] - grads[1]).abs().max() <= 2e-2 * grads[1].abs().max()
 
@@ -306,3 +306,77 @@ def test_train_step_from_prefetched_batches_equals_device_resident_batches(cuda_
     # (not bit-equal: cuDNN's weight-gradient kernels and the BatchNorm sums accumulate with atomics)
     assert torch.allclose(torch.tensor(losses[0]), torch.tensor(losses[1]), rtol=2e-3), losses
     assert len(set(round(v, 3) for v in losses[0])) >= 4, losses        # the batches really differ
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 8), (1, 6, 10, 16), (3, 32, 64, 64), (1, 2, 2, 8), (2, 64, 48, 24)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_native_maxpool_backward_matches_torch_including_ties(shape, cuda_device):
+    """Stem max-pool of the training step: forward bit-exact with F.max_pool2d, backward equal to torch's - the inputs are
+    ReLU-ed and coarsely quantised so that most windows hold ties (zeros, repeated values), which only the first-maximum
+    arg-max rule routes identically."""
+    from unet_watermark_b200.training import _MaxPoolFn
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    x = (torch.randn(n, c, h, w, generator=g).clamp_min(0) * 2).round() / 2      # values in {0, 0.5, 1, ...}
+    x = x.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(n, c, h // 2, w // 2, generator=g).to(cuda_device, torch.bfloat16)
+    gy = gy.contiguous(memory_format=torch.channels_last)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+    yr.backward(gy)
+    xo = x.clone().requires_grad_(True)
+    yo = _MaxPoolFn.apply(xo)
+    yo.backward(gy)
+    assert torch.equal(yo, yr)
+    # overlapping windows add up to four bf16 gradients in fp32, rounded once: equal up to the order of that sum
+    assert torch.allclose(xo.grad.float(), xr.grad.float(), rtol=1e-2, atol=1e-6)
+    assert (xo.grad == xr.grad).float().mean() > 0.999
+    assert torch.equal(xo.grad == 0, xr.grad == 0)                              # same arg-max positions
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 3, 3), (48, 96, 3, 3), (256, 64, 1, 1), (16, 16, 3, 3), (40, 24, 3, 3),
+                                   (512, 512, 3, 3), (64, 3, 7, 7), (8, 8, 2, 2)], ids=lambda s: "x".join(map(str, s)))
+def test_pack_train_weights_equals_the_torch_restatement(shape, cuda_device):
+    """One launch per conv and step: bf16 forward operand [Cout][taps][Cin] and data-gradient operand (training.dgrad_weights)."""
+    from unet_watermark_b200 import ops
+    from unet_watermark_b200.training import dgrad_weights
+    w = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape))).to(cuda_device)
+    w16 = w.to(torch.bfloat16)
+    fwd, dg = ops.pack_train_weights(w, True)
+    assert torch.equal(fwd, w16.permute(0, 2, 3, 1).reshape(shape[0], -1))
+    assert torch.equal(dg, dgrad_weights(w16))
+    fwd2, none = ops.pack_train_weights(w, False)
+    assert none is None and torch.equal(fwd2, fwd)
+
+
+def test_conv_fn_native_pack_switch_gives_the_same_gradients(cuda_device, monkeypatch):
+    from unet_watermark_b200.training import _ConvFn
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 24, 24, generator=g).to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(48, 32, 3, 3, generator=g).to(cuda_device) * 0.05
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("UWM_NATIVE_PACK", flag)
+        xi, wi = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = _ConvFn.apply(xi, wi, 1, 1)
+        y.float().square().sum().backward()
+        outs.append((y.detach(), xi.grad, wi.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-2, atol=1e-3)      # cuDNN's weight gradient may split K with atomics
+
+
+def test_copy_channels_between_slices_of_wider_buffers(cuda_device):
+    from unet_watermark_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    wide = torch.randn(2, 9, 7, 96, generator=g).to(cuda_device, torch.bfloat16)
+    dense = ops.copy_channels(wide[..., 32:80])                                  # slice -> new dense tensor
+    assert dense.is_contiguous() and torch.equal(dense, wide[..., 32:80])
+    out = torch.zeros(2, 9, 7, 128, dtype=torch.bfloat16, device=cuda_device)
+    ops.copy_channels(dense, out[..., 16:64])                                    # dense -> slice
+    ops.copy_channels(wide[..., 0:16], out[..., 96:112])                         # slice -> slice
+    want = torch.zeros_like(out)
+    want[..., 16:64] = wide[..., 32:80]
+    want[..., 96:112] = wide[..., 0:16]
+    assert torch.equal(out, want)
+    with pytest.raises(RuntimeError, match="copy_channels"):
+        ops.copy_channels(wide[..., 4:20])                                       # base address not 16-byte aligned

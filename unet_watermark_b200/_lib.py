@@ -102,6 +102,9 @@ SIGNATURES = {
     "uwm_bn_train_backward_nhwc_bf16": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P,
                                                   _P, _P, _P, _P]),
     "uwm_upsample2x_backward_nhwc_bf16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "uwm_maxpool3x3s2_backward_nhwc_bf16": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "uwm_pack_train_weights": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "uwm_copy_channels_nhwc_bf16": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, _P, C.c_int, _P]),
 }
 
 # exported only by the tools build (-DUWM_BENCH_TOOLS); bound when present

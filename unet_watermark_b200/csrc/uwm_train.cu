@@ -5,6 +5,9 @@
 //   bn_stats_kernel / bn_fwd_finalize_kernel / bn_apply_kernel        train-mode BatchNorm2d (+ residual)(+ ReLU), forward
 //   bn_bwd_reduce_kernel / bn_bwd_finalize_kernel / bn_bwd_apply_kernel   its backward (ReLU mask, d residual, dx, dgamma, dbeta)
 //   upsample2x_bwd_kernel                                              backward of F.interpolate(x2, nearest): 2x2 sum
+//   pack_train_weights_kernel                                          fp32 filter -> bf16 operands of the forward and the dgrad conv
+//   copy_channels_kernel                                               channel slices in / out of the decoder's concat buffers
+//   maxpool3x3s2_bwd_kernel                                            backward of the stem's MaxPool2d(3, 2, 1), arg-max recomputed
 //
 // All of it is HBM-bound: NHWC bf16, 16-byte accesses (8 channels per thread), fp32 arithmetic, per-channel sums
 // accumulated per thread in fp32, per block in shared memory and across blocks with fp64 atomics.  Algorithmic bytes per
@@ -336,6 +339,131 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restr
   }
 }
 
+// backward of MaxPool2d(3, stride 2, padding 1), no saved indices.  A thread owns a 2x2 block of input pixels (rows 2k,
+// 2k+1, columns 2j, 2j+1; 8 channels): the four windows that can route a gradient into it - (k,j), (k,j+1), (k+1,j),
+// (k+1,j+1) - lie inside the 5x5 neighbourhood around it, which is read once (25 16-byte loads for four pixels; from L1 /
+// L2 mostly - the tensor crosses HBM once) while the arg-max of each window is tracked with torch's rule: the FIRST
+// maximum in row-major scan order (strict '>' while scanning).  A pixel then sums the gradients of the windows whose
+// arg-max it is, in torch's order, in fp32.  (torch's max_pool_backward_nhwc: 0.54 ms of the step for this 134 MB tensor.)
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int n,
+                                                               int h, int w, int c, bf16* __restrict__ dx) {
+  const int groups = c / 8, oh_n = (h - 1) / 2 + 1, ow_n = (w - 1) / 2 + 1, bh = (h + 1) / 2, bw = (w + 1) / 2;
+  const long long items = (long long)n * bh * bw * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    long long t = idx / groups;
+    const int j = (int)(t % bw);
+    t /= bw;
+    const int k = (int)(t % bh);
+    const long long img = t / bh;
+    const bf16* xi = x + img * h * w * c + g * 8;
+    const bf16* dyi = dy + img * oh_n * ow_n * c + g * 8;
+    float mx[4][8];
+    int am[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        mx[q][e] = -INFINITY;
+        am[q][e] = -1;
+      }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const int yy = 2 * k - 1 + a;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        const int xx = 2 * j - 1 + b;
+        if (xx < 0 || xx >= w) continue;
+        float f[8];
+        unpack8(ld16(xi + ((long long)yy * w + xx) * c), f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                      // window q = (k + q / 2, j + q % 2): rows a in [2 (q / 2), +3)
+          const int a0 = 2 * (q >> 1), b0 = 2 * (q & 1);
+          if (a < a0 || a > a0 + 2 || b < b0 || b > b0 + 2) continue;     // compile-time after unrolling
+          const int id = (a - a0) * 3 + (b - b0);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (f[e] > mx[q][e]) {
+              mx[q][e] = f[e];
+              am[q][e] = id;
+            }
+        }
+      }
+    }
+    float d[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int oh = k + (q >> 1), ow = j + (q & 1);
+      if (oh < oh_n && ow < ow_n) {
+        unpack8(ld16(dyi + ((long long)oh * ow_n + ow) * c), d[q]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[q][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int yy = 2 * k + u, xx = 2 * j + v;
+        if (yy >= h || xx >= w) continue;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float s = am[0][e] == (1 + u) * 3 + 1 + v ? d[0][e] : 0.f;        // window (k, j): position (1 + u, 1 + v)
+          if (v == 1) s += am[1][e] == (1 + u) * 3 ? d[1][e] : 0.f;          // (k, j + 1): its first column
+          if (u == 1) s += am[2][e] == 1 + v ? d[2][e] : 0.f;                // (k + 1, j): its first row
+          if (u == 1 && v == 1) s += am[3][e] == 0 ? d[3][e] : 0.f;          // (k + 1, j + 1): its corner
+          acc[e] = s;
+        }
+        *reinterpret_cast<uint4*>(dx + (((long long)img * h + yy) * w + xx) * c + g * 8) = pack8(acc);
+      }
+  }
+}
+
+// Filters of a training-step conv, one launch per conv and step: the fp32 parameter [cout][cin][taps] becomes the bf16
+// UWM_PACK_TAPS operand of the forward conv, fwd[cout][taps][cin], and of the data-gradient conv (the same kernel run on
+// dy with the taps flipped and cin / cout exchanged), dgrad[cin][taps - 1 - t][cout].  A block stages 16 x 16 filters x taps
+// in shared memory: contiguous fp32 reads, 32-byte bf16 runs on both write sides (torch needed a cast + permute copy, a
+// flip and a transposing copy per conv: ~130 launches and 0.9 ms per step).
+constexpr int kWTile = 16;
+__global__ void __launch_bounds__(256) pack_train_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                                                 bf16* __restrict__ fwd, bf16* __restrict__ dgrad) {
+  extern __shared__ float tile[];                              // [16 cout][16 cin * taps + 1]
+  const int pitch = kWTile * taps + 1;
+  const int co0 = blockIdx.y * kWTile, ci0 = blockIdx.x * kWTile;
+  const int n_co = min(kWTile, cout - co0), n_ci = min(kWTile, cin - ci0);
+  const int tx = threadIdx.x & (kWTile - 1), ty = threadIdx.x / kWTile;      // 16 x 16 threads
+  if (ty < n_co) {
+    const float* src = w + ((size_t)(co0 + ty) * cin + ci0) * taps;           // n_ci * taps contiguous floats of filter row ty
+    for (int rem = tx; rem < n_ci * taps; rem += kWTile) tile[ty * pitch + rem] = __ldg(src + rem);
+  }
+  __syncthreads();
+  if (ty < n_co && tx < n_ci) {                                               // (ty, tx) = (cout, cin): runs along cin
+    bf16* dst = fwd + (size_t)(co0 + ty) * taps * cin + ci0 + tx;
+    for (int t = 0; t < taps; ++t) dst[(size_t)t * cin] = __float2bfloat16_rn(tile[ty * pitch + tx * taps + t]);
+  }
+  if (dgrad && ty < n_ci && tx < n_co) {                                      // (ty, tx) = (cin, cout): runs along cout
+    bf16* dst = dgrad + (size_t)(ci0 + ty) * taps * cout + co0 + tx;
+    for (int t = 0; t < taps; ++t) dst[(size_t)(taps - 1 - t) * cout] = __float2bfloat16_rn(tile[tx * pitch + ty * taps + t]);
+  }
+}
+
+// channels [0, c) of rows with pixel pitch src_pitch -> rows with pixel pitch dst_pitch, 16 bytes per thread: the skip half of
+// the decoder's concat (forward) and the skip's slice of the concat gradient (backward); torch's strided copy_ runs these
+// through its scalar elementwise kernel (13 launches, 0.52 ms per step).
+__global__ void __launch_bounds__(256) copy_channels_kernel(const bf16* __restrict__ src, long long src_pitch,
+                                                            bf16* __restrict__ dst, long long dst_pitch, long long pixels, int c) {
+  const int groups = c / 8;
+  const long long items = pixels * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (long long)gridDim.x * blockDim.x) {
+    const long long px = idx / groups;
+    const int g = (int)(idx - px * groups);
+    *reinterpret_cast<uint4*>(dst + px * dst_pitch + g * 8) = ld16(src + px * src_pitch + g * 8);
+  }
+}
+
 int check_bn(const char* who, const void* a, const void* b, long long pixels, int c) {
   if (!a || !b) return tfail(UWM_EINVAL, "%s: null tensor", who);
   if (pixels < 1) return tfail(UWM_EINVAL, "%s: pixels = %lld", who, pixels);
@@ -421,4 +549,55 @@ extern "C" int uwm_upsample2x_backward_nhwc_bf16(const void* d_dy, int n, int h,
   upsample2x_bwd_kernel<<<blocks, 256, 0, st>>>(static_cast<const bf16*>(d_dy), dy_pitch, n, h, w, c, static_cast<bf16*>(d_dx),
                                                 dx_pitch);
   return tpost("upsample2x_bwd_kernel");
+}
+
+extern "C" int uwm_maxpool3x3s2_backward_nhwc_bf16(const void* d_dy, const void* d_x, int n, int h, int w, int c, void* d_dx,
+                                                   void* stream) {
+  if (!d_dy || !d_x || !d_dx) return tfail(UWM_EINVAL, "maxpool3x3s2_backward: null tensor");
+  if (n < 1 || h < 1 || w < 1 || c < 8 || c % 8 != 0)
+    return tfail(UWM_EINVAL, "maxpool3x3s2_backward: bad geometry n=%d h=%d w=%d c=%d (channels a multiple of 8)", n, h, w, c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long items = (long long)n * h * w * (c / 8);
+  const int blocks = (int)std::max(1LL, std::min((items + 255) / 256, (long long)sm_count() * 16));
+  maxpool3x3s2_bwd_kernel<<<blocks, 256, 0, st>>>(static_cast<const bf16*>(d_dy), static_cast<const bf16*>(d_x), n, h, w, c,
+                                                  static_cast<bf16*>(d_dx));
+  return tpost("maxpool3x3s2_bwd_kernel");
+}
+
+extern "C" int uwm_pack_train_weights(const float* d_w, int cout, int cin, int kh, int kw, void* d_fwd, void* d_dgrad,
+                                      void* stream) {
+  if (!d_w || !d_fwd) return tfail(UWM_EINVAL, "pack_train_weights: null tensor");
+  const int taps = kh * kw;
+  if (cout < 1 || cin < 1 || kh < 1 || kw < 1 || taps > 49)
+    return tfail(UWM_EINVAL, "pack_train_weights: bad filter shape [%d,%d,%d,%d] (at most 49 taps)", cout, cin, kh, kw);
+  const size_t smem = (size_t)kWTile * (kWTile * taps + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool raised[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (!raised[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(pack_train_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      if (e != cudaSuccess) return tfail(UWM_ECUDA, "pack_train_weights: shared memory opt-in failed: %s", cudaGetErrorString(e));
+      raised[dev] = true;
+    }
+  }
+  dim3 grid((cin + kWTile - 1) / kWTile, (cout + kWTile - 1) / kWTile);
+  pack_train_weights_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(d_w, cout, cin, taps, static_cast<bf16*>(d_fwd),
+                                                                                  static_cast<bf16*>(d_dgrad));
+  return tpost("pack_train_weights_kernel");
+}
+
+extern "C" int uwm_copy_channels_nhwc_bf16(const void* d_src, long long pixels, int c, int src_pitch, void* d_dst, int dst_pitch,
+                                           void* stream) {
+  if (!d_src || !d_dst) return tfail(UWM_EINVAL, "copy_channels: null tensor");
+  if (pixels < 1 || c < 8 || c % 8 != 0 || src_pitch % 8 != 0 || dst_pitch % 8 != 0 || src_pitch < c || dst_pitch < c ||
+      (reinterpret_cast<uintptr_t>(d_src) & 15) || (reinterpret_cast<uintptr_t>(d_dst) & 15))
+    return tfail(UWM_EINVAL, "copy_channels: bad geometry pixels=%lld c=%d pitches %d/%d (channels, pitches and base addresses in units of 8 bf16)",
+                 pixels, c, src_pitch, dst_pitch);
+  const long long items = pixels * (c / 8);
+  const int blocks = (int)std::max(1LL, std::min((items + 255) / 256, (long long)sm_count() * 16));
+  copy_channels_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(d_src), src_pitch,
+                                                                             static_cast<bf16*>(d_dst), dst_pitch, pixels, c);
+  return tpost("copy_channels_kernel");
 }

@@ -318,3 +318,45 @@ def upsample2x_backward(dy: torch.Tensor) -> torch.Tensor:
     rc = lib.uwm_upsample2x_backward_nhwc_bf16(dy.data_ptr(), n, h2 // 2, w2 // 2, c, _pitch(dy), dx.data_ptr(), c, _stream())
     _lib.check(rc, "uwm_upsample2x_backward_nhwc_bf16")
     return dx
+
+
+def maxpool3x3s2_backward(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Backward of MaxPool2d(3, 2, 1): x [N,h,w,C] is the pool's input, dy [N,(h-1)//2+1,(w-1)//2+1,C] -> dx like x."""
+    _require_cuda(dy, x)
+    assert x.is_contiguous() and dy.is_contiguous() and x.dtype == dy.dtype == torch.bfloat16
+    n, h, w, c = x.shape
+    assert tuple(dy.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), (dy.shape, x.shape)
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    rc = lib.uwm_maxpool3x3s2_backward_nhwc_bf16(dy.data_ptr(), x.data_ptr(), n, h, w, c, dx.data_ptr(), _stream())
+    _lib.check(rc, "uwm_maxpool3x3s2_backward_nhwc_bf16")
+    return dx
+
+
+def pack_train_weights(weight: torch.Tensor, with_dgrad: bool):
+    """fp32 [Cout,Cin,kh,kw] -> (bf16 [Cout, kh*kw*Cin] forward operand, bf16 [Cin, kh*kw*Cout] flipped / transposed
+    data-gradient operand or None), one launch (``training.dgrad_weights`` is the torch restatement)."""
+    _require_cuda(weight)
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.dim() == 4
+    cout, cin, kh, kw = weight.shape
+    lib = _lib.load()
+    fwd = torch.empty(cout, kh * kw * cin, dtype=torch.bfloat16, device=weight.device)
+    dgrad = torch.empty(cin, kh * kw * cout, dtype=torch.bfloat16, device=weight.device) if with_dgrad else None
+    rc = lib.uwm_pack_train_weights(weight.data_ptr(), cout, cin, kh, kw, fwd.data_ptr(),
+                                    dgrad.data_ptr() if dgrad is not None else None, _stream())
+    _lib.check(rc, "uwm_pack_train_weights")
+    return fwd, dgrad
+
+
+def copy_channels(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NHWC bf16 channel slice -> channel slice (either side may be the slice of a wider buffer; ``dst`` None: a new dense
+    tensor)."""
+    _require_cuda(src, dst)
+    n, h, w, c = src.shape
+    if dst is None:
+        dst = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=src.device)
+    assert src.dtype == dst.dtype == torch.bfloat16 and tuple(dst.shape) == (n, h, w, c)
+    lib = _lib.load()
+    rc = lib.uwm_copy_channels_nhwc_bf16(src.data_ptr(), n * h * w, c, _pitch(src), dst.data_ptr(), _pitch(dst), _stream())
+    _lib.check(rc, "uwm_copy_channels_nhwc_bf16")
+    return dst

@@ -9,7 +9,8 @@ What runs where
             statistics, running-stat update) - so it cannot be folded into the conv as the inference plan does - on the
             hand-written HBM-bound kernels of csrc/uwm_train.cu, fused with the ReLU and the residual add (``_BNFn``;
             parameters and running statistics are the model's own ``nn.BatchNorm2d`` modules'); the decoder's nearest
-            upsample is written straight into the concat buffer (``_UpCatFn``); max-pool is a torch op.
+            upsample is written straight into the concat buffer (``_UpCatFn``); the stem's max-pool runs on the inference
+            path's kernel, its backward on ``maxpool3x3s2_bwd_kernel`` (``_MaxPoolFn``).
   backward  data gradients of the stride-1 convs (39 of the 45 convs of Unet-resnet34 that run on the C ABI) run on the same tcgen05
             kernel: dgrad of a 'same' conv is the conv of gy with the flipped, in/out-transposed filter (``dgrad_weights``;
             ``UWM_NATIVE_DGRAD=0`` turns it off).  Weight gradients, and the data gradients of the stride-2 convs, are
@@ -52,24 +53,32 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, stride, padding):
-        # one cast + permute launch: the channels_last bf16 filter IS the UWM_PACK_TAPS layout ([cout][kh*kw][cin]) and
-        # the layout cuDNN's weight-gradient call wants in the backward (three strided copies per conv before)
-        w16 = weight.detach().to(torch.bfloat16, memory_format=torch.channels_last)
+        cout, cin, kh, kw = weight.shape
+        w = weight.detach()
+        wd = None
+        if native_pack_enabled() and w.dtype == torch.float32 and w.is_contiguous():
+            # one launch: bf16 forward operand + (when the data gradient runs on the tcgen05 kernel) its flipped,
+            # in/out-transposed twin (csrc/uwm_train.cu pack_train_weights_kernel)
+            wp, wd = ops.pack_train_weights(w, ctx.needs_input_grad[0] and native_dgrad_applies(weight.shape, stride, padding))
+            w16 = wp.view(cout, kh, kw, cin).permute(0, 3, 1, 2)  # [cout,cin,kh,kw] with channels_last strides, no copy
+        else:
+            # the channels_last bf16 filter IS the UWM_PACK_TAPS layout ([cout][kh*kw][cin]) and the layout cuDNN's
+            # weight-gradient call wants in the backward
+            w16 = w.to(torch.bfloat16, memory_format=torch.channels_last)
+            wp = w16.permute(0, 2, 3, 1).reshape(cout, -1)
+            if not wp.is_contiguous():                            # (1x1 filters: strides of size-1 dims are ambiguous)
+                wp = wp.contiguous()
         xn = x.detach().permute(0, 2, 3, 1)                       # NHWC view of the channels_last tensor
         if not xn.is_contiguous():
             xn = xn.contiguous()
-        cout, _, kh, kw = weight.shape
-        wp = w16.permute(0, 2, 3, 1).reshape(cout, -1)
-        if not wp.is_contiguous():                                # (1x1 filters: strides of size-1 dims are ambiguous)
-            wp = wp.contiguous()
         y = ops.conv2d(xn, wp, _zero_bias(cout, x.device), kh, kw, stride, padding, relu=False)
-        ctx.save_for_backward(x, w16)
+        ctx.save_for_backward(x, w16, wd)
         ctx.conf = (stride, padding)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gy):
-        x, w16 = ctx.saved_tensors
+        x, w16, wd = ctx.saved_tensors
         stride, padding = ctx.conf
         gy = gy.contiguous(memory_format=torch.channels_last)
         need_gx = ctx.needs_input_grad[0]
@@ -78,13 +87,17 @@ class _ConvFn(torch.autograd.Function):
             # data gradient of a stride-1 'same' conv = the conv of gy with the spatially flipped, in/out-transposed
             # filter: the forward's own tcgen05 kernel, K = taps x Cout, N = Cin
             cin = w16.shape[1]
-            gx = ops.conv2d(gy.permute(0, 2, 3, 1), dgrad_weights(w16), _zero_bias(cin, gy.device),
+            gx = ops.conv2d(gy.permute(0, 2, 3, 1), wd if wd is not None else dgrad_weights(w16), _zero_bias(cin, gy.device),
                             w16.shape[2], w16.shape[3], 1, padding, relu=False).permute(0, 3, 1, 2)
             need_gx = False
         g2, gw, _ = torch.ops.aten.convolution_backward(
             gy, x, w16.contiguous(memory_format=torch.channels_last), None, [stride, stride], [padding, padding], [1, 1],
             False, [0, 0], 1, [need_gx, True, False])
         return (gx if gx is not None else g2), gw.float() if gw is not None else None, None, None
+
+
+def native_pack_enabled() -> bool:
+    return os.environ.get("UWM_NATIVE_PACK", "1") != "0"
 
 
 def native_dgrad_enabled() -> bool:
@@ -182,7 +195,7 @@ class _UpCatFn(torch.autograd.Function):
         out = torch.empty(n, 2 * h, 2 * w, cx + cs, dtype=xn.dtype, device=xn.device)
         ops.upsample2x(xn, out=out[..., :cx] if cs else out)
         if cs:
-            out[..., cx:].copy_(skip.detach().permute(0, 2, 3, 1))
+            ops.copy_channels(_nhwc(skip.detach()), out[..., cx:])
         ctx.cx, ctx.cs = cx, cs
         return out.permute(0, 3, 1, 2)
 
@@ -190,7 +203,9 @@ class _UpCatFn(torch.autograd.Function):
     def backward(ctx, g):
         gn = _nhwc(g)
         dx = ops.upsample2x_backward(gn[..., :ctx.cx] if ctx.cs else gn).permute(0, 3, 1, 2)
-        dskip = gn[..., ctx.cx:].permute(0, 3, 1, 2) if ctx.cs else None
+        # a dense copy of the skip's slice: its consumers (BatchNorm backward, the sum with the encoder-side gradient)
+        # would each re-gather the strided view through torch's scalar copy kernel
+        dskip = ops.copy_channels(gn[..., ctx.cx:]).permute(0, 3, 1, 2) if ctx.cs else None
         return dx, dskip
 
 
@@ -205,6 +220,30 @@ def _upcat(x: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
     return y.contiguous(memory_format=torch.channels_last)
 
 
+class _MaxPoolFn(torch.autograd.Function):
+    """MaxPool2d(3, 2, 1) of the stem (torchvision ResNet.maxpool): forward on the inference path's kernel (bit-exact with
+    ``F.max_pool2d``), backward on ``maxpool3x3s2_bwd_kernel`` with torch's first-maximum arg-max rule recomputed from
+    the saved input instead of an index tensor."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xn = _nhwc(x.detach())
+        ctx.save_for_backward(xn)
+        return ops.maxpool3x3s2(xn).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xn,) = ctx.saved_tensors
+        return ops.maxpool3x3s2_backward(_nhwc(gy), xn).permute(0, 3, 1, 2)
+
+
+def _maxpool(x: torch.Tensor) -> torch.Tensor:
+    if (os.environ.get("UWM_NATIVE_POOL", "1") != "0" and x.is_cuda and x.dtype == torch.bfloat16
+            and x.shape[1] % 8 == 0 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0):
+        return _MaxPoolFn.apply(x)
+    return F.max_pool2d(x, 3, 2, 1)
+
+
 def forward_train(model, x: torch.Tensor) -> torch.Tensor:
     """smp ``Unet.forward`` with BatchNorm in the module's current mode and autograd enabled.
     x: fp32 [B,3,H,W] (ImageNet-normalised) -> fp32 logits [B,1,H,W]."""
@@ -215,7 +254,7 @@ def forward_train(model, x: torch.Tensor) -> torch.Tensor:
     y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = _bn_relu(_conv(y, enc.conv1), enc.bn1)
     feats = [y]
-    y = F.max_pool2d(y, 3, 2, 1)
+    y = _maxpool(y)
     for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
         for blk in layer:
             idt = y
