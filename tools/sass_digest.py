@@ -42,7 +42,8 @@ def main():
     lines.append(hdr)
     for name, c in kernels.items():
         d = demangle(name)
-        d = re.sub(r"\(.*", "", d).replace("void ", "").replace("uwm::", "").replace("(anonymous namespace)::", "")
+        d = d.replace("(anonymous namespace)::", "")                  # before the argument list is cut at its '('
+        d = re.sub(r"\(.*", "", d).replace("void ", "").replace("uwm::", "")
         d = d.replace("(int)", "").replace("(bool)", "")
         lines.append(f"{d[:92]:<92s} {c['_total']:>7d} " + " ".join(f"{c[k]:>8d}" for k in KEYS[:10]))
         tot.update(c)
